@@ -1,0 +1,199 @@
+/*
+ * spd.h — C ABI of libspd.so, the B200 (sm_100a) implementation of Semi-PD's concurrent
+ * prefill + decode forward path.
+ *
+ * Every entry point is `extern "C"`, takes raw device pointers, explicit sizes / strides and the
+ * CUDA stream to launch on, performs no allocation and no host synchronisation (so the calls can
+ * be captured into CUDA graphs), and returns 0 on success, a positive cudaError_t on a CUDA
+ * failure, or a negative SPD_E_* code on an argument error.  Nothing here throws.  The text of
+ * the most recent failure on the calling thread is available from spd_last_error_string().
+ *
+ * Each declaration cites the reference interface it replaces.  Paths are relative to the
+ * reference checkout (infinigence/Semi-PD @ 2565f9f): S/ = python/sglang/srt/, K/ = sgl-kernel/.
+ */
+#ifndef SPD_H_
+#define SPD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* spd_stream_t; /* cudaStream_t */
+
+/* element types of activations / weights / KV pool */
+#define SPD_BF16 0
+#define SPD_F16 1
+
+/* argument-check error codes (CUDA errors are returned as positive cudaError_t values) */
+#define SPD_E_BADARG (-1)   /* null pointer, non-positive size, bad enum */
+#define SPD_E_ALIGN (-2)    /* pointer or stride not 16-byte aligned / dim not multiple of 8 */
+#define SPD_E_SHAPE (-3)    /* unsupported shape (head_dim, group size, K multiple …) */
+#define SPD_E_WORKSPACE (-4)/* workspace too small */
+#define SPD_E_DRIVER (-5)   /* driver entry point missing (green contexts, tensor maps) */
+
+/* ---------------------------------------------------------------------------------------------
+ * library / device
+ * ------------------------------------------------------------------------------------------- */
+int spd_version(void);
+const char* spd_last_error_string(void);
+/* replaces semi_pd_ipc.get_device_sm_count (semi-pd-ipc/ipc.cpp:87-92) */
+int spd_device_sm_count(int device, int* sm_count);
+
+/* ---------------------------------------------------------------------------------------------
+ * SM partitions — replaces the per-process MPS caps (CUDA_MPS_ACTIVE_THREAD_PERCENTAGE set in
+ * S/entrypoints/engine.py:591-593,632-634) with two CUDA green contexts that own DISJOINT SM
+ * sets inside one process.  `prefill_sms + decode_sms` may not exceed the device SM count; the
+ * driver rounds each group to its SM-group granularity and reports the granted counts.
+ * The returned streams belong to the partition; destroy with spd_partition_destroy.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct spd_partition spd_partition_t;
+int spd_partition_create(int device, int prefill_sms, int decode_sms, spd_partition_t** out);
+int spd_partition_sm_counts(const spd_partition_t* p, int* prefill_sms, int* decode_sms);
+/* which = 0: prefill stream, 1: decode stream */
+int spd_partition_stream(const spd_partition_t* p, int which, spd_stream_t* stream);
+int spd_partition_destroy(spd_partition_t* p);
+
+/* ---------------------------------------------------------------------------------------------
+ * elementwise ops — twins of torch.ops.sgl_kernel.* (K/csrc/torch_extension.cc:49-73)
+ * ------------------------------------------------------------------------------------------- */
+/* out[t,:] = x[t,:] * rsqrt(mean(x[t,:]^2) + eps) * w      (fp32 math)
+ * replaces sgl_kernel.rmsnorm (K/python/sgl_kernel/elementwise.py:9-19; semantics
+ * S/layers/layernorm.py:59-76).  Rows are `x_stride` / `out_stride` elements apart. */
+int spd_rmsnorm(void* out, const void* x, const void* w, int64_t tokens, int64_t dim,
+                int64_t x_stride, int64_t out_stride, float eps, int dtype, spd_stream_t stream);
+/* residual += x (rounded to dtype, stored) ; x = rmsnorm(residual) * w — both IN PLACE.
+ * replaces sgl_kernel.fused_add_rmsnorm (K/csrc/elementwise/fused_add_rms_norm_kernel.cu:24-55) */
+int spd_fused_add_rmsnorm(void* x, void* residual, const void* w, int64_t tokens, int64_t dim,
+                          float eps, int dtype, spd_stream_t stream);
+/* out[t, :d] = silu(x[t, :d]) * x[t, d:2d]
+ * replaces sgl_kernel.silu_and_mul (K/csrc/elementwise/activation.cu:36-50) */
+int spd_silu_and_mul(void* out, const void* x, int64_t tokens, int64_t d, int dtype,
+                     spd_stream_t stream);
+/* In-place rotary embedding of q [T, Hq, D] and k [T, Hk, D] (token strides in elements) using the
+ * fp32 cos_sin_cache [max_pos, rot_dim] (cos || sin) indexed by pos_ids [T] (int64).
+ * interleave = 0: NeoX halves, 1: GPT-J pairs.
+ * replaces sgl_kernel.apply_rope_pos_ids_cos_sin_cache (K/csrc/elementwise/rope.cu:22-89) */
+int spd_rope_inplace(void* q, void* k, const float* cos_sin_cache, const int64_t* pos_ids,
+                     int64_t tokens, int num_q_heads, int num_k_heads, int head_dim, int rot_dim,
+                     int64_t q_stride, int64_t k_stride, int interleave, int dtype,
+                     spd_stream_t stream);
+/* Fused: RoPE on q and k in place (as above) AND scatter of the rotated k rows and the v rows into
+ * the KV pool at out_cache_loc[t]:  k_pool[loc[t]] = k[t], v_pool[loc[t]] = v[t]  (pool rows are
+ * Hk*D contiguous elements).  Replaces rope (above) + MHATokenToKVPool.set_kv_buffer
+ * (S/mem_cache/memory_pool.py:316-346).  loc is int64. */
+int spd_rope_kvwrite(void* q, void* k, const void* v, void* k_pool, void* v_pool,
+                     const float* cos_sin_cache, const int64_t* pos_ids, const int64_t* loc,
+                     int64_t tokens, int num_q_heads, int num_k_heads, int head_dim, int rot_dim,
+                     int64_t q_stride, int64_t k_stride, int64_t v_stride, int interleave,
+                     int dtype, spd_stream_t stream);
+/* k_pool[loc[t]] = k[t]; v_pool[loc[t]] = v[t] — set_kv_buffer alone (S/mem_cache/memory_pool.py:316-346) */
+int spd_kv_write(const void* k, const void* v, void* k_pool, void* v_pool, const int64_t* loc,
+                 int64_t tokens, int64_t row_elems, int64_t k_stride, int64_t v_stride, int dtype,
+                 spd_stream_t stream);
+/* out[i, :] = table[idx[i], :]   (row_elems 16-bit elements per row; idx int64).
+ * Embedding lookup (S/layers/vocab_parallel_embedding.py:469-490) and the last-token gather of
+ * the logits processor (S/layers/logits_processor.py:244-262). */
+int spd_gather_rows(void* out, const void* table, const int64_t* idx, int64_t n, int64_t row_elems,
+                    int64_t table_rows, int dtype, spd_stream_t stream);
+/* ids[b] = argmax_v logits[b, v] (first maximal index, as torch.argmax) — greedy branch of
+ * Sampler.forward (S/layers/sampler.py:73-77,171).  logits fp32 [B, V] with row stride ld. */
+int spd_argmax_f32(int32_t* ids, const float* logits, int64_t batch, int64_t vocab, int64_t ld,
+                   spd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * batch metadata (integer work; bit-exact)
+ * ------------------------------------------------------------------------------------------- */
+/* positions[extend_start_loc[r] + j] = prefix_lens[r] + j ; extend_start_loc = exclusive cumsum of
+ * extend_lens.  Optionally (token_req != NULL) also writes the request index of every token.
+ * replaces compute_position_kernel (S/model_executor/forward_batch_info.py:393-446) */
+int spd_compute_positions(int64_t* positions, int32_t* extend_start_loc, int32_t* token_req,
+                          const int32_t* prefix_lens, const int32_t* extend_lens, int64_t batch,
+                          spd_stream_t stream);
+/* positions[b] = max(seq_lens[b] - 1, 0) — clamp_position (forward_batch_info.py:466-468) */
+int spd_decode_positions(int64_t* positions, const int64_t* seq_lens, int64_t batch,
+                         spd_stream_t stream);
+/* kv_indices[kv_indptr[b] + j] = req_to_token[req_pool_indices[b], kv_start[b] + j], j < lens[b]
+ * replaces create_flashinfer_kv_indices_triton (S/layers/attention/utils.py:5-39).
+ * kv_start may be NULL (= 0). req_pool_indices / lens int64 or int32 per `idx64`. */
+int spd_build_kv_indices(int32_t* kv_indices, const int32_t* req_to_token,
+                         const int64_t* req_pool_indices, const int32_t* lens,
+                         const int32_t* kv_indptr, const int32_t* kv_start, int64_t batch,
+                         int64_t req_to_token_stride, spd_stream_t stream);
+/* req_to_token[req[b], pre[b] + j] = out_cache_loc[cumsum(ext)[b] + j], j < ext[b]
+ * replaces write_req_to_token_pool_triton (S/managers/schedule_batch.py:1446-1480) */
+int spd_write_req_to_token(int32_t* req_to_token, const int64_t* req_pool_indices,
+                           const int64_t* pre_lens, const int64_t* seq_lens,
+                           const int64_t* extend_lens, const int64_t* out_cache_loc, int64_t batch,
+                           int64_t req_to_token_stride, spd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM — C[M,N] = A[M,K] * W[N,K]^T, 16-bit inputs, fp32 accumulation in TMEM (tcgen05 + TMA).
+ * replaces UnquantizedLinearMethod.apply = F.linear (S/layers/linear.py:165-172) for
+ * W_qkv / W_o / W_gate_up / W_down and the lm_head matmul (S/layers/logits_processor.py:416-419).
+ * lda/ldw/ldc are row strides in elements.  out_f32 != 0: C is fp32 holding the dtype-rounded
+ * result (== `.float()` of the 16-bit product, logits_processor.py:440).
+ * epilogue: SPD_EPI_NONE, or SPD_EPI_SILU_MUL: W is [2N, K] (gate rows || up rows, the
+ * MergedColumnParallelLinear order, S/models/llama.py:67-73) and C[M,N] = silu(A Wg^T) * (A Wu^T),
+ * both products rounded to dtype first (== gate_up_proj followed by SiluAndMul).
+ * workspace: device scratch for split-K partials (spd_gemm_workspace_bytes()); may be NULL when
+ * the call does not split.
+ * ------------------------------------------------------------------------------------------- */
+#define SPD_EPI_NONE 0
+#define SPD_EPI_SILU_MUL 1
+int64_t spd_gemm_workspace_bytes(void);
+int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_t K, int64_t lda,
+             int64_t ldw, int64_t ldc, int dtype, int out_f32, int epilogue, void* workspace,
+             int64_t workspace_bytes, int sm_budget, spd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * attention over the token-granular paged KV pool (page_size = 1; slot 0 is the dummy slot).
+ * Pool layout per layer: k_pool, v_pool [slots, Hk, D] (S/mem_cache/memory_pool.py:231-250).
+ * Slots of request r are req_to_token[req_pool_indices[r], 0 .. seq_len).
+ * ------------------------------------------------------------------------------------------- */
+/* Ragged chunked-prefill ("extend") attention, causal over [prefix || new]:
+ * query token j of request r (row extend_start_loc[r] + j of q) attends keys 0 .. prefix_r + j.
+ * The new tokens' K/V must already be in the pool.  q/out: [T, Hq, D], token stride in elements.
+ * replaces FlashInferAttnBackend.forward_extend's ragged + paged + merge_state kernels
+ * (S/layers/attention/flashinfer_backend.py:386-452); semantics
+ * S/layers/attention/torch_native_backend.py:26-109. */
+int spd_attn_prefill_ragged(void* out, const void* q, const void* k_pool, const void* v_pool,
+                            const int32_t* req_to_token, const int64_t* req_pool_indices,
+                            const int32_t* prefix_lens, const int32_t* extend_lens,
+                            const int32_t* extend_start_loc, int64_t batch, int64_t total_tokens,
+                            int64_t max_extend_len, int num_q_heads, int num_kv_heads,
+                            int head_dim, int64_t q_stride, int64_t out_stride,
+                            int64_t req_to_token_stride, float sm_scale, int dtype,
+                            spd_stream_t stream);
+/* Batched paged-decode attention: one query row per request over its seq_lens[b] cached rows
+ * (including the token just written).  Split-KV with an in-kernel merge; workspace from
+ * spd_attn_decode_workspace_bytes().  replaces FlashInferAttnBackend.forward_decode
+ * (flashinfer_backend.py:454-488); semantics torch_native_backend.py:111-179. */
+int64_t spd_attn_decode_workspace_bytes(int64_t max_batch, int num_q_heads, int head_dim);
+int spd_attn_decode_paged(void* out, const void* q, const void* k_pool, const void* v_pool,
+                          const int32_t* req_to_token, const int64_t* req_pool_indices,
+                          const int64_t* seq_lens, int64_t batch, int num_q_heads,
+                          int num_kv_heads, int head_dim, int64_t q_stride, int64_t out_stride,
+                          int64_t req_to_token_stride, float sm_scale, int dtype, void* workspace,
+                          int64_t workspace_bytes, int sm_budget, spd_stream_t stream);
+/* Plain SIMT implementations of the two calls above (no tensor cores).  Bring-up / on-device
+ * cross-check only; the product path never calls them. */
+int spd_attn_prefill_simt(void* out, const void* q, const void* k_pool, const void* v_pool,
+                          const int32_t* req_to_token, const int64_t* req_pool_indices,
+                          const int32_t* prefix_lens, const int32_t* extend_lens,
+                          const int32_t* extend_start_loc, int64_t batch, int64_t total_tokens,
+                          int64_t max_extend_len, int num_q_heads, int num_kv_heads, int head_dim,
+                          int64_t q_stride, int64_t out_stride, int64_t req_to_token_stride,
+                          float sm_scale, int dtype, spd_stream_t stream);
+int spd_attn_decode_simt(void* out, const void* q, const void* k_pool, const void* v_pool,
+                         const int32_t* req_to_token, const int64_t* req_pool_indices,
+                         const int64_t* seq_lens, int64_t batch, int num_q_heads, int num_kv_heads,
+                         int head_dim, int64_t q_stride, int64_t out_stride,
+                         int64_t req_to_token_stride, float sm_scale, int dtype, void* workspace,
+                         int64_t workspace_bytes, spd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPD_H_ */

@@ -1,0 +1,495 @@
+// C[M,N] = A[M,K] * W[N,K]^T on the 5th-generation tensor cores (tcgen05.mma, accumulators in
+// TMEM), operands staged by TMA into 128-byte-swizzled shared memory.  Replaces F.linear /
+// cuBLAS for W_qkv, W_o, W_gate_up, W_down and lm_head (S/layers/linear.py:165-172,
+// S/layers/logits_processor.py:416-419).
+//
+// One kernel, two regimes — both operands are K-major, so the same main loop serves either:
+//   * prefill regime (M > 256): D[128 x BN] tile = A_tile * W_tile^T, persistent CTAs walk the
+//     tile list M-fastest so the W tile of a column block is shared through L2.
+//   * decode regime (M <= 256), "swap-AB": D[128 x BN] = W_tile[128 rows of N] * A[BN >= M]^T,
+//     i.e. the weight dimension feeds UMMA-M (128 TMEM lanes) and the few tokens feed UMMA-N,
+//     so streaming the weights at HBM speed is the only cost; split-K spreads short N over all
+//     SMs, partials are summed in a fixed order by the last-arriving CTA (deterministic).
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global).
+// Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), TMEM double buffer full/empty
+// (MMA <-> epilogue).
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace spd {
+
+constexpr int kGemmThreads = 256;
+constexpr int kBM = 128;  // UMMA M (TMEM lanes)
+constexpr int kBK = 64;   // one 128-byte swizzle atom of 16-bit elements
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 220 * 1024;
+
+struct GemmParams {
+  void* C;
+  int64_t ldc;
+  int64_t x_rows;    // rows of the 128-lane operand (M normal, N swapped)
+  int64_t y_rows;    // rows of the BN operand
+  int64_t y_rows_w;  // SILU_MUL: offset (rows) of the "up" half inside W
+  int x_tiles, y_tiles, splits, kblocks;
+  int out_f32;
+  float* ws;        // split-K partials  [item][col][lane]
+  int* counters;    // one per tile
+};
+
+template <int BN>
+__host__ __device__ constexpr int gemm_stage_bytes() { return (kBM + BN) * kBK * 2; }
+template <int BN>
+__host__ __device__ constexpr int gemm_stages() {
+  return (kSmemBudget / gemm_stage_bytes<BN>()) < kMaxStages ? (kSmemBudget / gemm_stage_bytes<BN>())
+                                                             : kMaxStages;
+}
+template <int BN>
+__host__ __device__ constexpr int gemm_smem_bytes() {
+  return gemm_stages<BN>() * gemm_stage_bytes<BN>() + 1024 /*align*/ + 256 /*barriers*/;
+}
+
+// kSwap: D[i][j] -> C[j][n0+i]   else D[i][j] -> C[m0+i][n0+j]
+// kEpi == SPD_EPI_SILU_MUL (normal mode only): Y tile = [BN/2 gate rows | BN/2 up rows]
+template <typename T, int BN, bool kSwap, int kEpi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+            const GemmParams p) {
+  constexpr int kStages = gemm_stages<BN>();
+  constexpr int kXBytes = kBM * kBK * 2;
+  constexpr int kYBytes = BN * kBK * 2;
+  constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
+  constexpr int kBNOut = (kEpi == SPD_EPI_SILU_MUL) ? BN / 2 : BN;  // output columns per tile
+  constexpr int kChunk = BN >= 32 ? 32 : 16;
+  static_assert(!(kSwap && kEpi == SPD_EPI_SILU_MUL), "fused SiLU*mul only in the non-swapped regime");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sX = smem;
+  uint8_t* sY = smem + kStages * kXBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kXBytes + kYBytes));
+  uint64_t* full = bars;                     // [kStages]
+  uint64_t* empty = bars + kStages;          // [kStages]
+  uint64_t* tfull = bars + 2 * kStages;      // [2]
+  uint64_t* tempty = bars + 2 * kStages + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  int* flag_slot = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // everything above overlaps the previous kernel's tail under PDL
+  griddep_wait();
+
+  const int num_tiles = p.x_tiles * p.y_tiles;
+  const int total = num_tiles * p.splits;
+  const int kb_per = (p.kblocks + p.splits - 1) / p.splits;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // operand cache policy: in the decode regime the weights (X) stream through once
+      const uint64_t polX = kSwap ? kEvictFirst : kEvictNormal;
+      const uint64_t polY = kSwap ? kEvictLast : kEvictNormal;
+      int stage = 0, phase = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int tile = w / p.splits, split = w - tile * p.splits;
+        const int xt = tile % p.x_tiles, yt = tile / p.x_tiles;
+        const int kb0 = split * kb_per;
+        const int kb1 = min(kb0 + kb_per, p.kblocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], kXBytes + kYBytes);
+          tma_load_2d(sX + stage * kXBytes, &tmX, &full[stage], kb * kBK, xt * kBM, polX);
+          if constexpr (kEpi == SPD_EPI_SILU_MUL) {
+            tma_load_2d(sY + stage * kYBytes, &tmY, &full[stage], kb * kBK, yt * kBNOut, polY);
+            tma_load_2d(sY + stage * kYBytes + kYBytes / 2, &tmY, &full[stage], kb * kBK,
+                        static_cast<int>(p.y_rows_w) + yt * kBNOut, polY);
+          } else {
+            tma_load_2d(sY + stage * kYBytes, &tmY, &full[stage], kb * kBK, yt * BN, polY);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc<T>(kBM, BN, 0, 0);
+      int stage = 0, phase = 0, it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int tile = w / p.splits, split = w - tile * p.splits;
+        const int kb0 = split * kb_per;
+        const int kb1 = min(kb0 + kb_per, p.kblocks);
+        const int as = it & 1, aphase = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t xa = smem_u32(sX + stage * kXBytes);
+          const uint32_t ya = smem_u32(sY + stage * kYBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(xa + k * 32, 16, 1024);
+            const uint64_t bd = umma_desc_sw128(ya + k * 32, 16, 1024);
+            umma_ss(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // smem slot free once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[as]);  // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;     // D row == TMEM lane
+    const int et = threadIdx.x - 128;  // 0..127 among the epilogue threads
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int tile = w / p.splits, split = w - tile * p.splits;
+      const int xt = tile % p.x_tiles, yt = tile / p.x_tiles;
+      const int as = it & 1, aphase = (it >> 1) & 1;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      bool do_store = true;
+
+      if (p.splits > 1) {
+        // dump the fp32 partial, then the last-arriving split of this tile reduces all of them
+        float* mine = p.ws + (static_cast<size_t>(tile) * p.splits + split) * (kBM * BN);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += kChunk) {
+          uint32_t r[kChunk];
+          if constexpr (kChunk == 32) tmem_ld_32x32b_x32(taddr + c, r);
+          else tmem_ld_32x32b_x16(taddr + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j) mine[(c + j) * kBM + row] = __uint_as_float(r[j]);
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) *flag_slot = atomicAdd(&p.counters[tile], 1);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        do_store = (*flag_slot == p.splits - 1);
+        if (do_store) __threadfence();
+      }
+
+      if (do_store) {
+        const float* part = p.ws + static_cast<size_t>(tile) * p.splits * (kBM * BN);
+#pragma unroll 1
+        for (int c = 0; c < kBNOut; c += kChunk) {
+          float v[kChunk];
+          if (p.splits > 1) {
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) v[j] = 0.f;
+            for (int s = 0; s < p.splits; ++s) {
+              const float* ps = part + static_cast<size_t>(s) * (kBM * BN);
+#pragma unroll
+              for (int j = 0; j < kChunk; ++j) v[j] += __ldcg(&ps[(c + j) * kBM + row]);
+            }
+          } else {
+            uint32_t r[kChunk];
+            if constexpr (kChunk == 32) tmem_ld_32x32b_x32(taddr + c, r);
+            else tmem_ld_32x32b_x16(taddr + c, r);
+            if constexpr (kEpi == SPD_EPI_SILU_MUL) {
+              uint32_t u[kChunk];
+              tmem_ld_32x32b_x32(taddr + kBNOut + c, u);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < kChunk; ++j) {
+                // gate_up_proj output is rounded to T before SiluAndMul reads it
+                const float g = to_f32<T>(from_f32<T>(__uint_as_float(r[j])));
+                const float up = to_f32<T>(from_f32<T>(__uint_as_float(u[j])));
+                v[j] = g / (1.0f + __expf(-g)) * up;
+              }
+            } else {
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < kChunk; ++j) v[j] = __uint_as_float(r[j]);
+            }
+          }
+          if constexpr (!kSwap) {
+            const int64_t m = static_cast<int64_t>(xt) * kBM + row;
+            const int64_t n0 = static_cast<int64_t>(yt) * kBNOut + c;
+            if (m < p.x_rows) {
+              if (p.out_f32) {
+                float* dst = reinterpret_cast<float*>(p.C) + m * p.ldc + n0;
+#pragma unroll
+                for (int j = 0; j < kChunk; j += 4) {
+                  if (n0 + j < p.y_rows) {
+                    float4 o;
+                    o.x = to_f32<T>(from_f32<T>(v[j]));
+                    o.y = to_f32<T>(from_f32<T>(v[j + 1]));
+                    o.z = to_f32<T>(from_f32<T>(v[j + 2]));
+                    o.w = to_f32<T>(from_f32<T>(v[j + 3]));
+                    *reinterpret_cast<float4*>(dst + j) = o;
+                  }
+                }
+              } else {
+                T* dst = reinterpret_cast<T*>(p.C) + m * p.ldc + n0;
+#pragma unroll
+                for (int j = 0; j < kChunk; j += 8) {
+                  if (n0 + j < p.y_rows) {
+                    uint4 o;
+                    o.x = pack2<T>(v[j], v[j + 1]);
+                    o.y = pack2<T>(v[j + 2], v[j + 3]);
+                    o.z = pack2<T>(v[j + 4], v[j + 5]);
+                    o.w = pack2<T>(v[j + 6], v[j + 7]);
+                    *reinterpret_cast<uint4*>(dst + j) = o;
+                  }
+                }
+              }
+            }
+          } else {
+            // swapped: lane index runs along N (contiguous in C), column j is the token
+            const int64_t n = static_cast<int64_t>(xt) * kBM + row;
+            if (n < p.x_rows) {
+#pragma unroll
+              for (int j = 0; j < kChunk; ++j) {
+                const int64_t m = static_cast<int64_t>(yt) * BN + c + j;
+                if (m < p.y_rows) {
+                  if (p.out_f32)
+                    reinterpret_cast<float*>(p.C)[m * p.ldc + n] = to_f32<T>(from_f32<T>(v[j]));
+                  else
+                    reinterpret_cast<T*>(p.C)[m * p.ldc + n] = from_f32<T>(v[j]);
+                }
+              }
+            }
+          }
+        }
+        if (p.splits > 1) {
+          if (et == 0) p.counters[tile] = 0;  // re-arm for the next launch / graph replay
+        }
+      }
+      if (p.splits == 1) {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+      }
+    }
+  }
+
+  griddep_launch_dependents();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols, stride;
+  uint32_t box_rows;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && stride == o.stride &&
+           box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    h ^= k.rows * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= k.cols * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    h ^= k.stride * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
+    h ^= k.box_rows + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+// Descriptors are pure functions of (pointer, shape, box); cache them so steady-state launches
+// do no driver work.  Thread-safe: the prefill and decode workers call concurrently.
+int get_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t stride,
+             uint32_t box_rows) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{base, rows, cols, stride, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  CUtensorMap m;
+  int rc = make_tmap_2d_sw128(&m, base, rows, cols, stride, box_rows, kBK);
+  if (rc) return rc;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 8192) cache.clear();
+    cache[key] = m;
+  }
+  *out = m;
+  return 0;
+}
+
+constexpr int64_t kGemmWsBytes = 48ll << 20;  // split-K partials
+constexpr int kGemmCounters = 4096;
+
+template <typename T, int BN, bool kSwap, int kEpi>
+static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& ty, const GemmParams& p, int grid,
+                       cudaStream_t stream) {
+  auto kern = gemm_kernel<T, BN, kSwap, kEpi>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    SPD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  gemm_smem_bytes<BN>()));
+    configured = true;
+  }
+  SPD_CUDA(launch(kern, dim3(grid), dim3(kGemmThreads), gemm_smem_bytes<BN>(), stream,
+                  pdl_enabled(), tx, ty, p));
+  return 0;
+}
+
+}  // namespace spd
+
+using namespace spd;
+
+extern "C" {
+
+int64_t spd_gemm_workspace_bytes(void) { return kGemmWsBytes + kGemmCounters * 4; }
+
+int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_t K, int64_t lda,
+             int64_t ldw, int64_t ldc, int dtype, int out_f32, int epilogue, void* workspace,
+             int64_t workspace_bytes, int sm_budget, spd_stream_t stream) {
+  SPD_REQUIRE(C && A && W, SPD_E_BADARG, "spd_gemm: null pointer");
+  SPD_REQUIRE(M >= 0 && N > 0 && K > 0, SPD_E_BADARG, "spd_gemm: bad sizes M=%lld N=%lld K=%lld",
+              (long long)M, (long long)N, (long long)K);
+  SPD_REQUIRE(dtype == SPD_BF16 || dtype == SPD_F16, SPD_E_BADARG, "spd_gemm: bad dtype %d", dtype);
+  SPD_REQUIRE(epilogue == SPD_EPI_NONE || epilogue == SPD_EPI_SILU_MUL, SPD_E_BADARG,
+              "spd_gemm: bad epilogue %d", epilogue);
+  SPD_REQUIRE(K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % (out_f32 ? 4 : 8) == 0,
+              SPD_E_ALIGN, "spd_gemm: K, N and the leading dimensions must be multiples of 8");
+  SPD_REQUIRE(aligned16(A) && aligned16(W) && aligned16(C), SPD_E_ALIGN,
+              "spd_gemm: pointers must be 16-byte aligned");
+  SPD_REQUIRE(lda >= K && ldw >= K && ldc >= N, SPD_E_BADARG, "spd_gemm: leading dimension too small");
+  if (M == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  int sms = sm_budget > 0 ? sm_budget : device_sm_count_cached();
+  const int kblocks = static_cast<int>((K + kBK - 1) / kBK);
+
+  GemmParams p{};
+  p.C = C;
+  p.ldc = ldc;
+  p.kblocks = kblocks;
+  p.out_f32 = out_f32;
+  p.splits = 1;
+  p.ws = reinterpret_cast<float*>(workspace);
+  p.counters = workspace ? reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + kGemmWsBytes)
+                         : nullptr;
+  CUtensorMap tx, ty;
+  int rc;
+
+  const bool swap = (M <= 256) && epilogue == SPD_EPI_NONE;
+  if (swap) {
+    int BN = 16;
+    while (BN < M) BN <<= 1;  // 16,32,64,128,256
+    p.x_rows = N;
+    p.y_rows = M;
+    p.x_tiles = static_cast<int>((N + kBM - 1) / kBM);
+    p.y_tiles = 1;
+    // split-K so that every SM streams weights; keep >= 4 k-blocks per split
+    int splits = 1;
+    if (workspace && workspace_bytes >= spd_gemm_workspace_bytes() && p.x_tiles <= kGemmCounters) {
+      // cost model: rounds of equal work items per CTA, plus a small charge per extra split for
+      // the fp32 partial round trip (mostly L2)
+      const int max_by_k = kblocks / 4 > 0 ? kblocks / 4 : 1;
+      double best = 1e30;
+      for (int s = 1; s <= 16 && s <= max_by_k; ++s) {
+        if (static_cast<int64_t>(p.x_tiles) * s * kBM * BN * 4 > kGemmWsBytes) break;
+        // an empty trailing split would leave an accumulator undefined
+        if (s > 1 && (s - 1) * ((kblocks + s - 1) / s) >= kblocks) continue;
+        const int rounds = (p.x_tiles * s + sms - 1) / sms;
+        const double cost = static_cast<double>(rounds) / s + 0.03 * (s - 1);
+        if (cost < best - 1e-9) { best = cost; splits = s; }
+      }
+    }
+    p.splits = splits;
+    const int total = p.x_tiles * splits;
+    const int grid = total < sms ? total : sms;
+    if ((rc = get_tmap(&tx, W, N, K, ldw, kBM))) return rc;
+    if ((rc = get_tmap(&ty, A, M, K, lda, BN))) return rc;
+#define SPD_GEMM_SWAP(BN_)                                                               \
+  case BN_:                                                                              \
+    SPD_DISPATCH_DTYPE(dtype, { return launch_gemm<T, BN_, true, SPD_EPI_NONE>(tx, ty, p, grid, st); }); \
+    break;
+    switch (BN) {
+      SPD_GEMM_SWAP(16)
+      SPD_GEMM_SWAP(32)
+      SPD_GEMM_SWAP(64)
+      SPD_GEMM_SWAP(128)
+      SPD_GEMM_SWAP(256)
+    }
+#undef SPD_GEMM_SWAP
+    return set_error(SPD_E_SHAPE, "spd_gemm: unreachable BN=%d", BN);
+  }
+
+  p.x_rows = M;
+  p.y_rows = N;
+  p.x_tiles = static_cast<int>((M + kBM - 1) / kBM);
+  if (epilogue == SPD_EPI_SILU_MUL) {
+    constexpr int BN = 256;  // 128 gate + 128 up columns per tile
+    p.y_rows_w = N;
+    p.y_tiles = static_cast<int>((N + BN / 2 - 1) / (BN / 2));
+    const int total = p.x_tiles * p.y_tiles;
+    const int grid = total < sms ? total : sms;
+    if ((rc = get_tmap(&tx, A, M, K, lda, kBM))) return rc;
+    if ((rc = get_tmap(&ty, W, 2 * N, K, ldw, BN / 2))) return rc;
+    SPD_DISPATCH_DTYPE(dtype, { return launch_gemm<T, BN, false, SPD_EPI_SILU_MUL>(tx, ty, p, grid, st); });
+  }
+  {
+    // 128 x 256 tiles unless that leaves most SMs idle, then 128 x 128
+    const int tiles256 = p.x_tiles * static_cast<int>((N + 255) / 256);
+    const bool use256 = tiles256 >= sms || N % 256 == 0;
+    const int BN = use256 ? 256 : 128;
+    p.y_tiles = static_cast<int>((N + BN - 1) / BN);
+    const int total = p.x_tiles * p.y_tiles;
+    const int grid = total < sms ? total : sms;
+    if ((rc = get_tmap(&tx, A, M, K, lda, kBM))) return rc;
+    if ((rc = get_tmap(&ty, W, N, K, ldw, BN))) return rc;
+    if (use256) {
+      SPD_DISPATCH_DTYPE(dtype, { return launch_gemm<T, 256, false, SPD_EPI_NONE>(tx, ty, p, grid, st); });
+    } else {
+      SPD_DISPATCH_DTYPE(dtype, { return launch_gemm<T, 128, false, SPD_EPI_NONE>(tx, ty, p, grid, st); });
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"
