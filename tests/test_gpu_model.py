@@ -1,0 +1,105 @@
+"""End-to-end parity of the CUDA path (through ModelRunner.forward, i.e. through the C-ABI) with
+the CPU oracle on identical synthetic weights and inputs.  Criterion (BASELINE.json north_star):
+max-abs(logits_gpu - logits_cpu_fp32) < 1e-2 in fp16, greedy ids exact where the oracle's
+top-1/top-2 margin exceeds 2e-2.  bf16 is held to 6e-2 (its 8-bit mantissa alone moves O(1)
+logits by ~2^-8 per rounding point)."""
+import pytest
+import torch
+
+from oracle import llama_oracle as O
+from tests.helpers import GpuSession, make_runner
+
+pytestmark = pytest.mark.gpu
+
+TINY = dict(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+            num_key_value_heads=2, head_dim=128, vocab_size=1024, max_position_embeddings=2048)
+# Llama-3-8B head / FFN shapes, 2 layers, small vocab (SURVEY §8d "exhaustive parity" model)
+L8B2 = dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=2, num_attention_heads=32,
+            num_key_value_heads=8, head_dim=128, vocab_size=4096, max_position_embeddings=4096)
+TOL = {torch.float16: 1e-2, torch.bfloat16: 6e-2}
+
+
+def _prompts(lens, vocab, off=7):
+    return [[(off + 13 * i + 31 * j) % vocab for i in range(n)] for j, n in enumerate(lens)]
+
+
+def _check_ids(logits_cpu, ids_gpu, margin=2e-2):
+    top2 = logits_cpu.topk(2, dim=-1).values
+    safe = (top2[:, 0] - top2[:, 1]) > margin
+    ref = logits_cpu.argmax(-1)
+    assert torch.equal(ids_gpu.long()[safe], ref[safe])
+    return int(safe.sum())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("cfg", [TINY, L8B2], ids=["tiny", "8b-2layer"])
+def test_extend_then_decode_matches_oracle(cfg, dtype):
+    mr, oracle, ocfg = make_runner(cfg, dtype)
+    gs, os_ = GpuSession(mr), O.OracleSession(oracle, 4096, 17)
+    lens = [5, 1, 130, 64, 257]
+    prompts = _prompts(lens, cfg["vocab_size"])
+    reqs, lg, ids = gs.extend(prompts)
+    rids, lc, _ = os_.extend(prompts)
+    assert (lg - lc).abs().max().item() < TOL[dtype]
+    n_safe = _check_ids(lc, ids)
+    tok = lc.argmax(-1).tolist()  # feed both sides the oracle's tokens
+    for _ in range(4):
+        lg, ids = gs.decode(reqs, tok)
+        lc, _ = os_.decode(rids, tok)
+        assert (lg - lc).abs().max().item() < TOL[dtype]
+        n_safe += _check_ids(lc, ids)
+        tok = lc.argmax(-1).tolist()
+    assert n_safe > 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float16])
+def test_chunked_prefill_with_prefix(dtype):
+    """Second chunk runs with prefix_len > 0: one fused pass over [prefix pages ‖ new tokens]."""
+    mr, oracle, _ = make_runner(L8B2, dtype)
+    gs, os_ = GpuSession(mr), O.OracleSession(oracle, 4096, 17)
+    p = _prompts([300, 40], L8B2["vocab_size"])
+    reqs, _, _ = gs.extend([p[0][:170], p[1][:39]])
+    rids, _, _ = os_.extend([p[0][:170], p[1][:39]])
+    _, lg, ids = gs.extend([p[0][170:], p[1][39:]], reqs)
+    _, lc, _ = os_.extend([p[0][170:], p[1][39:]], rids)
+    assert (lg - lc).abs().max().item() < TOL[dtype]
+    _check_ids(lc, ids)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16])
+def test_cuda_graph_decode_with_padding(dtype):
+    """bs = 3 replays the bs = 4 graph: padded row has seq_len 1 and writes the dummy slot 0
+    (cuda_graph_runner.py:467-478); results equal the eager path and the oracle."""
+    mr, oracle, _ = make_runner(TINY, dtype, cuda_graph=True, cuda_graph_bs=[1, 2, 4, 8])
+    assert mr.cuda_graph_runner is not None
+    gs, os_ = GpuSession(mr), O.OracleSession(oracle, 4096, 17)
+    prompts = _prompts([9, 33, 2], TINY["vocab_size"])
+    reqs, lg, _ = gs.extend(prompts)
+    rids, lc, _ = os_.extend(prompts)
+    tok = lc.argmax(-1).tolist()
+    for _ in range(3):
+        lg, ids = gs.decode(reqs, tok)
+        assert mr.cuda_graph_runner.bs == 4 and mr.cuda_graph_runner.raw_bs == 3
+        lc, _ = os_.decode(rids, tok)
+        assert (lg - lc).abs().max().item() < TOL[dtype]
+        _check_ids(lc, ids)
+        tok = lc.argmax(-1).tolist()
+
+
+def test_greedy_generation_token_exact():
+    """16-token greedy continuation, GPU tokens fed back to the GPU and oracle tokens to the
+    oracle: sequences must be identical while every step's margin is > 2e-2."""
+    mr, oracle, _ = make_runner(TINY, torch.float16)
+    gs, os_ = GpuSession(mr), O.OracleSession(oracle, 4096, 17)
+    prompts = _prompts([16], TINY["vocab_size"])
+    reqs, lg, ids = gs.extend(prompts)
+    rids, lc, _ = os_.extend(prompts)
+    g_tok, c_tok = ids.tolist(), lc.argmax(-1).tolist()
+    for _ in range(16):
+        top2 = lc.topk(2, -1).values
+        if (top2[:, 0] - top2[:, 1]).min().item() <= 2e-2:
+            break
+        assert g_tok == c_tok
+        lg, ids = gs.decode(reqs, g_tok)
+        lc, _ = os_.decode(rids, c_tok)
+        g_tok, c_tok = ids.tolist(), lc.argmax(-1).tolist()
