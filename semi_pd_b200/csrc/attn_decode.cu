@@ -1,8 +1,509 @@
-// placeholder until the tcgen05 decode kernel lands (next commit)
+// Batched paged-decode attention on tcgen05 — a PERSISTENT, HBM-streaming kernel.
+// One query row per request over its seq_len cached rows (torch_native_backend.py:111-179);
+// replaces flashinfer's BatchDecodeWithPagedKVCacheWrapper + its host-side plan()
+// (S/layers/attention/flashinfer_backend.py:454-488,627-674).
+//
+// Swap-AB formulation (tcgen05's minimum M is 64, a decode (request, kv-head) pair has only
+// G = Hq/Hk <= 8 query rows):
+//     S^T[128 kv x 16] = K_tile[128 kv x D] * Q_g^T        (kv rows feed UMMA-M, heads feed N)
+//     O^T[D x 16]     += V_tile^T[D x 128 kv] * P^T         (V is the MN-major A operand)
+// so every K/V byte is read from HBM exactly once, straight into swizzled smem, and consumed by
+// the tensor core; the 16-wide N makes the MMAs ~60 cycles per 64 KB tile — the kernel's only
+// real cost is the stream itself.
+//
+// grid = #SMs (or the partition's SM budget); each CTA walks work items (request, kv head,
+// kv split) with a static stride and keeps its TMEM, barriers and the 3-stage K/V ring alive
+// across items, so the gather of the next item overlaps the epilogue of the current one.
+// Splits are merged by the last-arriving CTA of a (request, kv head) pair — no host plan, no
+// second launch, CUDA-graph safe (counters re-arm themselves).
+//
+// warps 0-3: softmax over TMEM lanes (column reductions via shuffles + smem), O rescale, epilogue
+// warps 4-7: K/V gather through req_to_token (16-byte cp.async, 128-byte swizzle), Q staging
+// warp  8  : MMA issuer + TMEM allocator
+#include <cuda.h>
+
 #include "common.cuh"
+#include "ptx.cuh"
+
+namespace spd {
+
+constexpr int kDcThreads = 288;
+constexpr int kDcTile = 128;   // kv tokens per tile
+constexpr int kDcD = 128;      // head dim
+constexpr int kDcN = 16;       // UMMA N (>= GQA group)
+constexpr int kDcStages = 3;
+constexpr int kDcTileBytes = 128 * 128 * 2;
+constexpr int kDcQBytes = 16 * 128 * 2;   // [16 rows x 128 d] as two 2 KB swizzle blocks
+constexpr int kDcSmem = kDcStages * 2 * kDcTileBytes + 2 * kDcQBytes + 2 * kDcQBytes + 1024 + 1024;
+constexpr int kDcMaxSplits = 32;
+constexpr int kDcMaxGroup = 8;
+
+struct DecodeParams {
+  void* out;
+  const void* q;
+  const void* k_pool;
+  const void* v_pool;
+  const int32_t* req_to_token;
+  const int64_t* req_pool_indices;
+  const int64_t* seq_lens;
+  int batch, Hq, Hk, splits;
+  int64_t q_stride, out_stride, rtt_stride;
+  float scale_log2;
+  float* o_part;   // [b][Hq][splits][D]
+  float* ml_part;  // [b][Hq][splits][2]
+  int* counters;   // [b][Hk]
+};
+
+struct DcItem {
+  int b, hk, split, t0, t1, n_tiles;
+};
+
+__device__ __forceinline__ DcItem dc_item(const DecodeParams& p, int w) {
+  DcItem it;
+  it.split = w % p.splits;
+  const int r = w / p.splits;
+  it.hk = r % p.Hk;
+  it.b = r / p.Hk;
+  const int L = static_cast<int>(p.seq_lens[it.b]);
+  int per = (L + p.splits - 1) / p.splits;
+  per = (per + kDcTile - 1) / kDcTile * kDcTile;
+  it.t0 = it.split * per;
+  it.t1 = min(L, it.t0 + per);
+  it.n_tiles = it.t1 > it.t0 ? (it.t1 - it.t0 + kDcTile - 1) / kDcTile : 0;
+  return it;
+}
+
+// walks the CTA's global tile sequence: (item, tile within item).  `iter` counts NON-EMPTY items
+// only: it selects the Q / O double buffers, and consecutive non-empty items must alternate.
+struct DcCursor {
+  int w, iter, j;
+  DcItem item;
+  bool valid;
+  __device__ __forceinline__ void init(const DecodeParams& p, int total) {
+    w = blockIdx.x;
+    iter = 0;
+    j = 0;
+    settle(p, total);
+  }
+  __device__ __forceinline__ void settle(const DecodeParams& p, int total) {
+    valid = false;
+    while (w < total) {
+      item = dc_item(p, w);
+      if (item.n_tiles > 0) { valid = true; return; }
+      w += gridDim.x;  // empty items carry no tiles (the softmax warps still publish them)
+    }
+  }
+  __device__ __forceinline__ void next(const DecodeParams& p, int total) {
+    if (++j >= item.n_tiles) {
+      j = 0;
+      w += gridDim.x;
+      ++iter;
+      settle(p, total);
+    }
+  }
+};
+
+__device__ __forceinline__ uint32_t dc_tile_off(int row, int chunk16) {
+  return (chunk16 >> 3) * 16384 + row * 128 + (((chunk16 & 7) ^ (row & 7)) << 4);
+}
+// [16 rows x 128 cols] 16-bit, two [16 x 128 B] swizzle blocks of 2 KB
+__device__ __forceinline__ uint32_t dc_small_off(int row, int col) {
+  const int chunk = col >> 3;
+  return (chunk >> 3) * 2048 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4) + (col & 7) * 2;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kDcThreads, 1)
+attn_decode_kernel(const DecodeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sK = smem;                                    // 3 x 32 KB
+  uint8_t* sV = smem + kDcStages * kDcTileBytes;         // 3 x 32 KB
+  uint8_t* sQ = smem + 2 * kDcStages * kDcTileBytes;     // 2 x 4 KB
+  uint8_t* sP = sQ + 2 * kDcQBytes;                      // 2 x 4 KB
+  uint8_t* misc = sP + 2 * kDcQBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
+  uint64_t* kv_full = bars;        // 3
+  uint64_t* kv_empty = bars + 3;   // 3
+  uint64_t* s_full = bars + 6;     // 2
+  uint64_t* s_empty = bars + 8;    // 2
+  uint64_t* p_full = bars + 10;    // 2
+  uint64_t* p_empty = bars + 12;   // 2
+  uint64_t* o_done = bars + 14;    // 1
+  uint64_t* o_empty = bars + 15;   // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  int* flag_slot = reinterpret_cast<int*>(tmem_slot + 1);
+  float* red = reinterpret_cast<float*>(misc + 256);  // [2 parity][2 (max,sum)][4 warps][8 heads]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int G = p.Hq / p.Hk;
+  const int total = p.batch * p.Hk * p.splits;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int i = 0; i < kDcStages; ++i) {
+        mbar_init(&kv_full[i], 128);
+        mbar_init(&kv_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&s_empty[i], 4);
+        mbar_init(&p_full[i], 4);
+        mbar_init(&p_empty[i], 1);
+        mbar_init(&o_empty[i], 4);
+      }
+      mbar_init(o_done, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 64);
+    tmem_relinquish();
+  }
+  // zero P / Q staging once: rows >= G are never written and only feed ignored output columns
+  for (int i = threadIdx.x; i < (4 * kDcQBytes) / 16; i += kDcThreads)
+    reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;        // 2 x 16 columns
+  const uint32_t tmem_O = tmem_base + 32;   // 2 x 16 columns
+
+  griddep_wait();
+
+  if (warp == 8) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc<T>(128, kDcN, 0, 0);  // A = K (K-major), B = Q (K-major)
+      constexpr uint32_t idesc_o = umma_idesc<T>(128, kDcN, 1, 0);  // A = V (MN-major), B = P^T (K-major)
+      DcCursor cs, cp;  // cs runs one tile ahead of cp
+      cs.init(p, total);
+      cp.init(p, total);
+      int ts = 0;  // global tile counter of the S stream
+      auto issue_s = [&]() {
+        const int st = ts % kDcStages, sb = ts & 1;
+        mbar_wait(&kv_full[st], (ts / kDcStages) & 1);
+        mbar_wait(&s_empty[sb], ((ts >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t k_addr = smem_u32(sK + st * kDcTileBytes);
+        const uint32_t q_addr = smem_u32(sQ + (cs.iter & 1) * kDcQBytes);
+#pragma unroll
+        for (int k = 0; k < kDcD / 16; ++k) {
+          umma_ss(tmem_S + sb * kDcN,
+                  umma_desc_sw128(k_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                  umma_desc_sw128(q_addr + (k >> 2) * 2048 + (k & 3) * 32, 16, 1024), idesc_s,
+                  k > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[sb]);
+        ++ts;
+        cs.next(p, total);
+      };
+      if (cs.valid) issue_s();
+      int tp = 0;  // global tile counter of the PV stream
+      int o_uses[2] = {0, 0};
+      while (cp.valid) {
+        if (cs.valid) issue_s();
+        const int st = tp % kDcStages, pb = tp & 1, ob = cp.iter & 1;
+        mbar_wait(&p_full[pb], (tp >> 1) & 1);
+        if (cp.j == 0) {
+          mbar_wait(&o_empty[ob], (o_uses[ob] & 1) ^ 1);
+          ++o_uses[ob];
+        }
+        tc_fence_after_sync();
+        const uint32_t v_addr = smem_u32(sV + st * kDcTileBytes);
+        const uint32_t p_addr = smem_u32(sP + pb * kDcQBytes);
+#pragma unroll
+        for (int k = 0; k < kDcTile / 16; ++k) {
+          umma_ss(tmem_O + ob * kDcN, umma_desc_sw128(v_addr + k * 2048, 16384, 1024),
+                  umma_desc_sw128(p_addr + (k >> 2) * 2048 + (k & 3) * 32, 16, 1024), idesc_o,
+                  (cp.j > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(&p_empty[pb]);
+        umma_commit(o_done);
+        ++tp;
+        cp.next(p, total);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== K/V gather + Q staging (128 threads) =====================
+    const int lt = threadIdx.x - 128;
+    const int chunk = lt & 15;
+    const int rsub = lt >> 4;
+    const T* kp = reinterpret_cast<const T*>(p.k_pool);
+    const T* vp = reinterpret_cast<const T*>(p.v_pool);
+    const int64_t row_elems = static_cast<int64_t>(p.Hk) * kDcD;
+    DcCursor c;
+    c.init(p, total);
+    int t = 0;
+    int prev_stage = -1;
+    while (c.valid) {
+      const int st = t % kDcStages;
+      mbar_wait(&kv_empty[st], ((t / kDcStages) & 1) ^ 1);
+      const DcItem& it = c.item;
+      if (c.j == 0) {
+        // stage the G query rows of this (request, kv head) as the K-major B operand
+        if (rsub < G) {
+          const T* src = reinterpret_cast<const T*>(p.q) + it.b * p.q_stride +
+                         (static_cast<int64_t>(it.hk) * G + rsub) * kDcD + chunk * 8;
+          const uint4 v = *reinterpret_cast<const uint4*>(src);
+          *reinterpret_cast<uint4*>(sQ + (c.iter & 1) * kDcQBytes + dc_small_off(rsub, chunk * 8)) = v;
+        }
+      }
+      const int32_t* rtt = p.req_to_token + p.req_pool_indices[it.b] * p.rtt_stride;
+      const int64_t col = static_cast<int64_t>(it.hk) * kDcD + chunk * 8;
+      const uint32_t kdst = smem_u32(sK + st * kDcTileBytes);
+      const uint32_t vdst = smem_u32(sV + st * kDcTileBytes);
+      const int tok0 = it.t0 + c.j * kDcTile;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int row = i * 8 + rsub;
+        const int tok = tok0 + row;
+        const bool valid = tok < it.t1;
+        const int64_t slot = valid ? rtt[tok] : 0;
+        const uint32_t off = dc_tile_off(row, chunk);
+        cp_async16(kdst + off, kp + slot * row_elems + col, valid);
+        cp_async16(vdst + off, vp + slot * row_elems + col, valid);
+      }
+      cp_async_commit();
+      // publish the PREVIOUS tile (keeps two tiles = 128 KB in flight per SM)
+      if (prev_stage >= 0) {
+        cp_async_wait<1>();
+        fence_proxy_async_smem();
+        mbar_arrive(&kv_full[prev_stage]);
+      }
+      prev_stage = st;
+      ++t;
+      c.next(p, total);
+    }
+    if (prev_stage >= 0) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      mbar_arrive(&kv_full[prev_stage]);
+    }
+  } else {
+    // ===================== softmax / correction / epilogue =====================
+    const int tid = threadIdx.x;  // TMEM lane: kv token within tile (S^T) or head-dim index (O^T)
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    int t = 0;  // global tile counter
+    int iter = 0;  // non-empty items seen so far (same convention as DcCursor::iter)
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const DcItem it = dc_item(p, w);
+      float m_run[kDcMaxGroup], l_run[kDcMaxGroup];
+#pragma unroll
+      for (int g = 0; g < kDcMaxGroup; ++g) { m_run[g] = -INFINITY; l_run[g] = 0.f; }
+      const int ob = iter & 1;
+      for (int j = 0; j < it.n_tiles; ++j, ++t) {
+        const int sb = t & 1;
+        mbar_wait(&s_full[sb], (t >> 1) & 1);
+        tc_fence_after_sync();
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_S + lane_base + sb * kDcN, r);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[sb]);
+        const bool valid = (it.t0 + j * kDcTile + tid) < it.t1;
+        float s[kDcMaxGroup];
+        float* rmax = red + (t & 1) * 64;
+        float* rsum = rmax + 32;
+#pragma unroll
+        for (int g = 0; g < kDcMaxGroup; ++g) {
+          s[g] = valid ? __uint_as_float(r[g]) * p.scale_log2 : -INFINITY;
+          const float wm = warp_max(s[g]);
+          if (lane == 0) rmax[warp * 8 + g] = wm;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float alpha[kDcMaxGroup], pv[kDcMaxGroup];
+        bool any_rescale = false;
+#pragma unroll
+        for (int g = 0; g < kDcMaxGroup; ++g) {
+          const float mt = fmaxf(fmaxf(rmax[g], rmax[8 + g]), fmaxf(rmax[16 + g], rmax[24 + g]));
+          const float m_new = fmaxf(m_run[g], mt);  // finite: every tile has >= 1 valid token
+          alpha[g] = (m_run[g] == -INFINITY) ? 0.f : fast_exp2(m_run[g] - m_new);
+          any_rescale |= (g < G) && (alpha[g] != 1.f);
+          m_run[g] = m_new;
+          // round to the operand type first so that l matches what the tensor core multiplies
+          pv[g] = to_f32<T>(from_f32<T>(fast_exp2(s[g] - m_new)));
+          const float ws = warp_sum(pv[g]);
+          if (lane == 0) rsum[warp * 8 + g] = ws;
+        }
+        // P^T -> smem (B operand, K-major: row = head, col = kv token)
+        mbar_wait(&p_empty[sb], ((t >> 1) & 1) ^ 1);
+        uint8_t* pdst = sP + sb * kDcQBytes;
+#pragma unroll
+        for (int g = 0; g < kDcMaxGroup; ++g)
+          if (g < G) *reinterpret_cast<T*>(pdst + dc_small_off(g, tid)) = from_f32<T>(pv[g]);
+        // O^T rescale needs PV_{t-1} complete
+        if (j > 0) {
+          mbar_wait(o_done, (t - 1) & 1);
+          tc_fence_after_sync();
+          if (any_rescale) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(tmem_O + lane_base + ob * kDcN, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < kDcMaxGroup; ++g)
+              o[g] = __float_as_uint(__uint_as_float(o[g]) * alpha[g]);
+            tmem_st_32x32b_x16(tmem_O + lane_base + ob * kDcN, o);
+            tmem_st_wait();
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // also publishes rsum
+        if (lane == 0) mbar_arrive(&p_full[sb]);
+#pragma unroll
+        for (int g = 0; g < kDcMaxGroup; ++g) {
+          const float st_ = (rsum[g] + rsum[8 + g]) + (rsum[16 + g] + rsum[24 + g]);
+          l_run[g] = l_run[g] * alpha[g] + st_;
+        }
+      }
+      // ---- epilogue of this item ----
+      float o[kDcMaxGroup];
+      if (it.n_tiles > 0) {
+        mbar_wait(o_done, (t - 1) & 1);
+        tc_fence_after_sync();
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_O + lane_base + ob * kDcN, r);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[ob]);
+#pragma unroll
+        for (int g = 0; g < kDcMaxGroup; ++g) o[g] = __uint_as_float(r[g]);
+        ++iter;
+      } else {
+#pragma unroll
+        for (int g = 0; g < kDcMaxGroup; ++g) o[g] = 0.f;
+      }
+      if (p.splits == 1) {
+        T* dst = reinterpret_cast<T*>(p.out) + it.b * p.out_stride +
+                 static_cast<int64_t>(it.hk) * G * kDcD + tid;
+#pragma unroll
+        for (int g = 0; g < kDcMaxGroup; ++g)
+          if (g < G) dst[g * kDcD] = from_f32<T>(l_run[g] > 0.f ? o[g] / l_run[g] : 0.f);
+      } else {
+#pragma unroll
+        for (int g = 0; g < kDcMaxGroup; ++g)
+          if (g < G) {
+            const int64_t idx = (static_cast<int64_t>(it.b) * p.Hq + it.hk * G + g) * p.splits + it.split;
+            p.o_part[idx * kDcD + tid] = o[g];
+            if (tid == 0) { p.ml_part[idx * 2] = m_run[g]; p.ml_part[idx * 2 + 1] = l_run[g]; }
+          }
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0) *flag_slot = atomicAdd(&p.counters[it.b * p.Hk + it.hk], 1);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*flag_slot == p.splits - 1) {
+          // last split of this (request, kv head): merge all partials in split order
+          __threadfence();
+#pragma unroll 1
+          for (int g = 0; g < G; ++g) {
+            const int64_t base = (static_cast<int64_t>(it.b) * p.Hq + it.hk * G + g) * p.splits;
+            float M = -INFINITY;
+            for (int s2 = 0; s2 < p.splits; ++s2) M = fmaxf(M, __ldcg(&p.ml_part[(base + s2) * 2]));
+            float num = 0.f, den = 0.f;
+            for (int s2 = 0; s2 < p.splits; ++s2) {
+              const float mm = __ldcg(&p.ml_part[(base + s2) * 2]);
+              const float ll = __ldcg(&p.ml_part[(base + s2) * 2 + 1]);
+              if (ll > 0.f) {
+                const float wgt = fast_exp2(mm - M);
+                num += wgt * __ldcg(&p.o_part[(base + s2) * kDcD + tid]);
+                den += wgt * ll;
+              }
+            }
+            reinterpret_cast<T*>(p.out)[it.b * p.out_stride +
+                                        (static_cast<int64_t>(it.hk) * G + g) * kDcD + tid] =
+                from_f32<T>(den > 0.f ? num / den : 0.f);
+          }
+          if (tid == 0) p.counters[it.b * p.Hk + it.hk] = 0;  // re-arm for the next launch
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // flag_slot is reused by the next item
+      }
+    }
+  }
+
+  griddep_launch_dependents();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 64);
+}
+
+int check_attn_args(const char* fn, const void* out, const void* q, const void* k_pool,
+                    const void* v_pool, const void* rtt, const void* rpi, int Hq, int Hk, int D,
+                    int64_t q_stride, int64_t out_stride);
+
+}  // namespace spd
+
 using namespace spd;
-extern "C" int spd_attn_decode_paged(void*, const void*, const void*, const void*, const int32_t*,
-                                     const int64_t*, const int64_t*, int64_t, int, int, int, int64_t,
-                                     int64_t, int64_t, float, int, void*, int64_t, int, spd_stream_t) {
-  return set_error(SPD_E_SHAPE, "spd_attn_decode_paged: not built yet");
+
+extern "C" int spd_attn_decode_paged(void* out, const void* q, const void* k_pool,
+                                     const void* v_pool, const int32_t* req_to_token,
+                                     const int64_t* req_pool_indices, const int64_t* seq_lens,
+                                     int64_t batch, int num_q_heads, int num_kv_heads, int head_dim,
+                                     int64_t q_stride, int64_t out_stride,
+                                     int64_t req_to_token_stride, float sm_scale, int dtype,
+                                     void* workspace, int64_t workspace_bytes, int sm_budget,
+                                     spd_stream_t stream) {
+  int rc = check_attn_args("spd_attn_decode_paged", out, q, k_pool, v_pool, req_to_token,
+                           req_pool_indices, num_q_heads, num_kv_heads, head_dim, q_stride, out_stride);
+  if (rc) return rc;
+  SPD_REQUIRE(seq_lens && batch >= 0, SPD_E_BADARG, "spd_attn_decode_paged: bad seq_lens/batch");
+  SPD_REQUIRE(head_dim == kDcD, SPD_E_SHAPE,
+              "spd_attn_decode_paged: head_dim must be 128 on the tcgen05 path (got %d)", head_dim);
+  if (batch == 0) return 0;
+  const int sms = sm_budget > 0 ? sm_budget : device_sm_count_cached();
+  DecodeParams p{};
+  p.out = out;
+  p.q = q;
+  p.k_pool = k_pool;
+  p.v_pool = v_pool;
+  p.req_to_token = req_to_token;
+  p.req_pool_indices = req_pool_indices;
+  p.seq_lens = seq_lens;
+  p.batch = static_cast<int>(batch);
+  p.Hq = num_q_heads;
+  p.Hk = num_kv_heads;
+  p.q_stride = q_stride;
+  p.out_stride = out_stride;
+  p.rtt_stride = req_to_token_stride;
+  p.scale_log2 = sm_scale * 1.4426950408889634f;
+  // KV splits: balance equal-sized work items over the persistent CTAs (lengths are device-side,
+  // so the choice depends on the launch shape only — nothing to plan on the host per step)
+  const int64_t pairs = batch * num_kv_heads;
+  int splits = 1;
+  {
+    double best = 1e30;
+    for (int s = 1; s <= kDcMaxSplits; ++s) {
+      const int64_t items = pairs * s;
+      const int64_t rounds = (items + sms - 1) / sms;
+      const double cost = static_cast<double>(rounds) / s + 0.02 * (s - 1);
+      if (cost < best - 1e-9) { best = cost; splits = s; }
+    }
+  }
+  p.splits = splits;
+  if (splits > 1) {
+    SPD_REQUIRE(workspace && workspace_bytes >= spd_attn_decode_workspace_bytes(batch, num_q_heads, head_dim),
+                SPD_E_WORKSPACE, "spd_attn_decode_paged: workspace too small (%lld bytes)",
+                (long long)workspace_bytes);
+    p.o_part = reinterpret_cast<float*>(workspace);
+    p.ml_part = p.o_part + batch * num_q_heads * kDcMaxSplits * head_dim;
+    p.counters = reinterpret_cast<int*>(p.ml_part + batch * num_q_heads * kDcMaxSplits * 2);
+  }
+  const int64_t total = pairs * splits;
+  const int grid = static_cast<int>(total < sms ? total : sms);
+  SPD_DISPATCH_DTYPE(dtype, {
+    auto kern = attn_decode_kernel<T>;
+    static bool configured = false;
+    if (!configured) {
+      SPD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDcSmem));
+      configured = true;
+    }
+    SPD_CUDA(launch(kern, dim3(grid), dim3(kDcThreads), kDcSmem, as_stream(stream), pdl_enabled(), p));
+  });
+  return 0;
 }

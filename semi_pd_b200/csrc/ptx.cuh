@@ -288,6 +288,13 @@ __device__ __forceinline__ float2 unpack2<__half>(uint32_t w) {
   return __half22float2(*reinterpret_cast<__half2*>(&w));
 }
 
+// 2^x on the SFU (ex2.approx: max rel. error 2^-22, exact 0 for very negative x, inf stays inf)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -11,4 +11,9 @@ namespace spd {
 int make_tmap_2d_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                        uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
 
+// Cached variant (implemented in gemm.cu): descriptors are pure functions of (pointer, shape,
+// box), so steady-state launches do no driver work.  box_cols is fixed at 64 (one swizzle atom).
+int get_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t stride,
+             uint32_t box_rows);
+
 }  // namespace spd
