@@ -342,7 +342,10 @@ class LlamaOracle:
             h, residual = rmsnorm(h, w[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps, residual)
             gate_up = F.linear(h, w[p + "mlp.gate_up_proj.weight"])
             h = F.linear(silu_and_mul(gate_up), w[p + "mlp.down_proj.weight"])
-        h, _ = rmsnorm(h, w["model.norm.weight"], cfg.rms_norm_eps, residual)
+        if residual is None:  # zero-layer model (bench.py uses it to time embedding + lm_head alone)
+            h = rmsnorm(h, w["model.norm.weight"], cfg.rms_norm_eps)
+        else:
+            h, _ = rmsnorm(h, w["model.norm.weight"], cfg.rms_norm_eps, residual)
         if not b.is_decode:
             last = torch.cumsum(torch.tensor(b.extend_seq_lens, dtype=torch.int64), 0) - 1
             h = h[last]

@@ -103,8 +103,16 @@ def _load():
 lib = _load()
 
 
+class _Counter:
+    """Kernel launches issued through the C-ABI by this process (bench.py's `gpu_launches`).
+    Every successful compute entry point is one kernel launch; replays of a captured CUDA graph
+    are accounted by CudaGraphRunner (kernels per graph x replays)."""
+    launches = 0
+
+
 def check(rc: int, what: str = "") -> None:
     """Raise RuntimeError for a non-zero return code, carrying the library's error text."""
+    _Counter.launches += 1
     if rc != 0:
         msg = lib.spd_last_error_string().decode("utf-8", "replace")
         raise RuntimeError(f"libspd {what} failed (code {rc}): {msg}")

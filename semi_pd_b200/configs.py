@@ -60,7 +60,7 @@ _PRESETS = {
     "llama-3-70b": dict(hidden_size=8192, intermediate_size=28672, num_hidden_layers=80,
                         num_attention_heads=64, num_key_value_heads=8),
     "tiny-llama-test": dict(hidden_size=256, intermediate_size=512, num_hidden_layers=2,
-                            num_attention_heads=8, num_key_value_heads=2, head_dim=64,
+                            num_attention_heads=4, num_key_value_heads=2, head_dim=128,
                             vocab_size=1024, max_position_embeddings=2048),
     # one 8B-shaped layer pair: exhaustive parity at real head/FFN shapes
     "llama-3-8b-2layer": dict(num_hidden_layers=2, vocab_size=4096),

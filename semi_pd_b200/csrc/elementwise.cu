@@ -55,7 +55,7 @@ __device__ __forceinline__ float block_sum(float v, float* smem) {
 // (kMaxVec 16-byte vectors per thread) so HBM traffic is exactly 1 read + 1 write per tensor.
 // ------------------------------------------------------------------------------------------------
 constexpr int kNormThreads = 256;
-constexpr int kMaxVec = 4;  // rows up to 256*4*8 = 8192 elements stay in registers
+constexpr int kMaxVec = 8;  // rows up to 256*8*8 = 16384 elements stay in registers
 
 template <typename T, bool kFusedAdd>
 __global__ void __launch_bounds__(kNormThreads)

@@ -19,6 +19,7 @@ from typing import Optional
 import torch
 
 from . import ops
+from ._lib import _Counter
 from .attention_backend import SpdAttnBackend
 from .configs import InstanceRole, ModelConfig, ServerArgs, default_cuda_graph_bs
 from .distributed import init_distributed_environment, new_tp_group
@@ -200,6 +201,7 @@ class CudaGraphRunner:
         self.model_runner = model_runner
         self.graphs = {}
         self.output_buffers = {}
+        self.kernels_per_graph = {}
         sa = model_runner.server_args
         bs_list = sa.cuda_graph_bs or default_cuda_graph_bs(sa.cuda_graph_max_bs)
         self.capture_bs = sorted(b for b in bs_list if b <= model_runner.req_to_token_pool.size)
@@ -248,8 +250,10 @@ class CudaGraphRunner:
             run_once()
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
+        n0 = _Counter.launches
         with torch.cuda.graph(graph, pool=self.pool, stream=stream if stream != torch.cuda.default_stream() else None):
             out = run_once()
+        self.kernels_per_graph[bs] = _Counter.launches - n0  # libspd kernels inside this graph
         self.pool = graph.pool()
         torch.cuda.synchronize()
         return graph, out
@@ -276,6 +280,7 @@ class CudaGraphRunner:
         if not skip_attn_backend_init:
             self.replay_prepare(forward_batch)
         self.graphs[self.bs].replay()
+        _Counter.launches += self.kernels_per_graph[self.bs]
         next_token_logits, next_ids = self.output_buffers[self.bs]
         # greedy ids were computed inside the graph
         return LogitsProcessorOutput(next_token_logits=next_token_logits[: self.raw_bs],

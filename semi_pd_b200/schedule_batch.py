@@ -45,6 +45,8 @@ class Req:
         self.is_chunked = 0
         self.is_retracted = False
         self.finished_reason: Optional[str] = None
+        # tokens whose computation has been launched (>= len(output_ids) under the overlap loop)
+        self.launched_tokens = 0
         # timing (host clock, seconds)
         self.arrival_time = arrival_time
         self.first_token_time: Optional[float] = None
@@ -158,7 +160,12 @@ class ScheduleBatch:
             for r, i in zip(reqs, req_pool_indices):
                 r.req_pool_idx = i
 
-        self.input_ids = self._h2d([t for ids in input_ids for t in ids], torch.int64)
+        if all(getattr(r, "input_ids_device", None) is not None for r in reqs):
+            # prompt ids already resident in HBM (bench.py's device-resident arm): slice, no H2D
+            parts = [r.input_ids_device[len(r.prefix_indices):len(r.fill_ids)] for r in reqs]
+            self.input_ids = parts[0] if len(parts) == 1 else torch.cat(parts)
+        else:
+            self.input_ids = self._h2d([t for ids in input_ids for t in ids], torch.int64)
         self.req_pool_indices = self._h2d(req_pool_indices, torch.int64)
         self.seq_lens = self._h2d(seq_lens, torch.int64)
         prefix_lens_t = self._h2d(prefix_lens, torch.int64)

@@ -1,0 +1,545 @@
+"""Semi-PD schedulers and launcher — the caller of the hot path, kept protocol-compatible with
+the reference (python/sglang/srt/managers/semi_pd_scheduler.py:326-432,
+semi_pd_prefill_scheduler.py:74-173, semi_pd_decode_scheduler.py:90-377,
+entrypoints/engine.py:540-728) but re-shaped for one process per GPU:
+
+  reference                                   here
+  ------------------------------------------  ---------------------------------------------------
+  2 OS processes per GPU (P, D)               2 threads, one CUDA context
+  MPS caps via CUDA_MPS_ACTIVE_THREAD_PERC.   2 CUDA green contexts with DISJOINT SM sets
+  cudaIpcMemHandle export of weights/KV       one weight set + one KV pool, addressed directly
+  ZMQ pickles, P blocks on D's loop           in-process queues; D pre-admits prefill batches so P
+                                              never waits a decode step (removes the TTFT floor)
+  no GPU-side ordering of req_to_token        CUDA events ride on the two batch messages
+
+The decode scheduler remains the single memory authority (admission, request + KV slot
+allocation, retraction); the prefill scheduler only runs forwards into slots D chose and returns
+the first token ids.
+"""
+from __future__ import annotations
+
+import collections
+import logging
+import queue
+import threading
+import time
+from typing import Deque, Dict, List, Optional
+
+import torch
+
+from . import ops
+from .configs import (DECODE_ENGINE_SM_PERCENTILE, PREFILL_ENGINE_SM_PERCENTILE, InstanceRole,
+                      ModelConfig, ServerArgs, get_model_config)
+from .io_struct import (BatchProcessPrefillResultReq, GetNextPrefillBatchInput,
+                        GetNextPrefillBatchOutput, TokenizedGenerateReqInput)
+from .schedule_batch import Req, SamplingParams, ScheduleBatch
+from .schedule_policy import AddReqResult, PrefillAdder
+from .tp_worker import TpModelWorker
+
+logger = logging.getLogger(__name__)
+
+# python/sglang/global_config.py:24-32
+DEFAULT_INIT_NEW_TOKEN_RATIO = 0.7
+DEFAULT_MIN_NEW_TOKEN_RATIO_FACTOR = 0.14
+DEFAULT_NEW_TOKEN_RATIO_DECAY_STEPS = 600
+RETRACT_DECODE_STEPS = 20
+
+
+class SemiPDScheduler:
+    """State shared by both roles (managers/semi_pd_scheduler.py:40-216)."""
+
+    def __init__(self, server_args: ServerArgs, worker: TpModelWorker, stream: torch.cuda.Stream,
+                 sm_budget: int, role: InstanceRole):
+        self.server_args = server_args
+        self.tp_worker = worker
+        self.stream = stream
+        self.sm_budget = sm_budget
+        self.role = role
+        self.device = worker.device
+        self.req_to_token_pool, self.token_to_kv_pool_allocator = worker.get_memory_pool()
+        self.waiting_queue: List[Req] = []
+        self.inbox: "queue.Queue" = queue.Queue()
+        self.stop_flag = threading.Event()
+        self.error: Optional[BaseException] = None
+        self.forward_ct = 0
+        # bench.py's device-resident arm: prompt ids are sliced from HBM and sampled ids never
+        # leave the device (completion is by launch count); off for normal serving
+        self.device_resident = False
+
+    def handle_generate_request(self, recv_req: TokenizedGenerateReqInput):
+        req = Req(recv_req.rid, recv_req.input_ids, recv_req.sampling_params,
+                  arrival_time=recv_req.arrival_time)
+        req.input_ids_device = recv_req.input_ids_device
+        if recv_req.is_retracted:
+            self.waiting_queue.insert(0, req)  # semi_pd_scheduler.py:52-56
+        else:
+            self.waiting_queue.append(req)
+        return req
+
+    def _thread_setup(self):
+        torch.cuda.set_device(self.device)
+        ops.set_sm_budget(self.sm_budget)
+
+    def run(self):
+        try:
+            self._thread_setup()
+            with torch.cuda.stream(self.stream):
+                self.event_loop()
+        except BaseException as e:  # noqa: BLE001  (reference: SIGQUIT to the parent, engine.py:407-413)
+            logger.exception("scheduler %s died", self.role)
+            self.error = e
+            self.stop_flag.set()
+
+
+class SemiPDPrefillScheduler(SemiPDScheduler):
+    """managers/semi_pd_prefill_scheduler.py:74-173."""
+
+    def __init__(self, server_args, worker, stream, sm_budget, d_inbox: "queue.Queue"):
+        super().__init__(server_args, worker, stream, sm_budget, InstanceRole.PREFILL)
+        self.send_to_d_instance = d_inbox
+        self.bridge_socket: "queue.Queue" = queue.Queue()  # D -> P: GetNextPrefillBatchOutput
+        self.chunked_rid: Optional[str] = None
+        self.prefill_tokens = 0
+        self.prefill_busy_s = 0.0
+
+    def recv_requests(self):
+        while True:
+            try:
+                msg = self.inbox.get_nowait()
+            except queue.Empty:
+                return
+            if isinstance(msg, TokenizedGenerateReqInput):
+                self.handle_generate_request(msg)
+
+    def to_extend_batch(self, resp: GetNextPrefillBatchOutput) -> ScheduleBatch:
+        by_rid = {r.rid: r for r in self.waiting_queue}
+        can_run_list = [by_rid[rid] for rid in resp.rids]
+        # requests of this batch are fully prefilled afterwards — except the one D marked as still
+        # chunked, which stays queued for its next chunk (prefill_scheduler.py:79-95)
+        done = set(resp.rids) - ({resp.chunked_rid} if resp.chunked_rid else set())
+        self.waiting_queue = [r for r in self.waiting_queue if r.rid not in done]
+        self.chunked_rid = resp.chunked_rid
+        for i, r in enumerate(can_run_list):
+            r.extend_input_len = resp.extend_input_lens[i]
+            pre_len = resp.prefix_lens[i]
+            r.prefix_indices = [0] * pre_len
+            r.fill_ids = r.origin_input_ids[: pre_len + r.extend_input_len]
+        batch = ScheduleBatch.init_new(can_run_list, self.req_to_token_pool,
+                                       self.token_to_kv_pool_allocator, self.device)
+        batch.prepare_for_extend(pre_allocated_req_pool_indices=resp.req_pool_indices)
+        return batch
+
+    def event_loop(self):
+        """event_loop_normal: P always runs the non-overlapped loop (semi_pd_scheduler.py:422-427)."""
+        while not self.stop_flag.is_set():
+            try:
+                resp = self.bridge_socket.get(timeout=0.002)
+            except queue.Empty:
+                continue
+            self.recv_requests()
+            t0 = time.perf_counter()
+            if resp.ready_event is not None:
+                self.stream.wait_event(resp.ready_event)
+            batch = self.to_extend_batch(resp)
+            mwb = batch.get_model_worker_batch()
+            _, next_token_ids = self.tp_worker.forward_batch_generation(mwb)
+            self.forward_ct += 1
+            self.process_batch_result_prefill(batch, next_token_ids)
+            self.prefill_tokens += mwb.extend_num_tokens
+            self.prefill_busy_s += time.perf_counter() - t0
+
+    def process_batch_result_prefill(self, batch: ScheduleBatch, next_token_ids: torch.Tensor):
+        if self.device_resident:
+            ids = next_token_ids.to(torch.int64)  # stays in HBM; D consumes it after done_event
+        else:
+            ids = next_token_ids.tolist()  # the only host sync of the prefill worker
+        done = torch.cuda.Event()
+        done.record(self.stream)
+        if self.device_resident:
+            # no D2H copy, but D must not merge these requests before their KV exists — otherwise
+            # the running decode batch would stall on the device behind this prefill
+            done.synchronize()
+        self.send_to_d_instance.put(BatchProcessPrefillResultReq(next_token_ids=ids, done_event=done))
+
+
+class SemiPDDecodeScheduler(SemiPDScheduler):
+    """managers/semi_pd_decode_scheduler.py:90-377 + the overlap loop of scheduler.py:559-597."""
+
+    MAX_INFLIGHT_PREFILL_BATCHES = 2
+
+    def __init__(self, server_args, worker, stream, sm_budget):
+        super().__init__(server_args, worker, stream, sm_budget, InstanceRole.DECODE)
+        self.send_to_p_instance: Optional["queue.Queue"] = None  # P's inbox (retracted requests)
+        self.bridge_socket: Optional["queue.Queue"] = None       # D -> P batch descriptions
+        self.running_batch = ScheduleBatch.init_new([], self.req_to_token_pool,
+                                                    self.token_to_kv_pool_allocator, self.device)
+        self.scheduled_prefill_batches: Deque[ScheduleBatch] = collections.deque()
+        self.chunked_req: Optional[Req] = None
+        self.max_running_requests = worker.max_running_requests
+        self.max_prefill_tokens = server_args.max_prefill_tokens
+        self.chunked_prefill_size = server_args.chunked_prefill_size
+        self.init_new_token_ratio = min(DEFAULT_INIT_NEW_TOKEN_RATIO * server_args.schedule_conservativeness, 1.0)
+        self.min_new_token_ratio = min(self.init_new_token_ratio * DEFAULT_MIN_NEW_TOKEN_RATIO_FACTOR, 1.0)
+        self.new_token_ratio_decay = ((self.init_new_token_ratio - self.min_new_token_ratio)
+                                      / DEFAULT_NEW_TOKEN_RATIO_DECAY_STEPS)
+        self.new_token_ratio = self.init_new_token_ratio
+        self.finished: "queue.Queue[Req]" = queue.Queue()
+        self.num_finished = 0
+        self.decode_tokens = 0
+        self.decode_steps = 0
+        self.result_queue: Deque = collections.deque()
+        self._pinned_ring = [torch.empty((4096,), dtype=torch.int32, pin_memory=True) for _ in range(4)]
+        self._ring_i = 0
+        self.token_callback = None  # optional: fn(req, token_id, finished) — the detokenizer hook
+
+    # ---- inbound -------------------------------------------------------------------------------
+    def recv_requests(self):
+        while True:
+            try:
+                msg = self.inbox.get_nowait()
+            except queue.Empty:
+                return
+            if isinstance(msg, TokenizedGenerateReqInput):
+                self.handle_generate_request(msg)
+            elif isinstance(msg, BatchProcessPrefillResultReq):
+                self.process_prefill_result(msg)
+            elif isinstance(msg, GetNextPrefillBatchInput):
+                self.get_next_prefill_batch(msg)
+
+    # ---- prefill admission (D decides, P computes) ------------------------------------------------
+    def propose_prefill_candidates(self) -> List[str]:
+        """The rule the reference's P uses to pick what it asks for (prefill_scheduler.py:123-129)."""
+        n, cands = 0, []
+        for r in self.waiting_queue:
+            if n > self.chunked_prefill_size:
+                break
+            n += len(r.origin_input_ids)
+            cands.append(r.rid)
+        return cands
+
+    def maybe_schedule_prefill(self):
+        while (len(self.scheduled_prefill_batches) < self.MAX_INFLIGHT_PREFILL_BATCHES
+               and (self.waiting_queue or self.chunked_req is not None)):
+            before = len(self.scheduled_prefill_batches)
+            self.get_next_prefill_batch(GetNextPrefillBatchInput(rids=self.propose_prefill_candidates()))
+            if len(self.scheduled_prefill_batches) == before:
+                break
+
+    def get_new_batch_prefill(self, rids: List[str]) -> Optional[ScheduleBatch]:
+        if (getattr(self.running_batch, "batch_is_full", False) or not self.waiting_queue) \
+                and self.chunked_req is None:
+            return None
+        inflight = sum(len(b.reqs) for b in self.scheduled_prefill_batches)
+        running_bs = len(self.running_batch.reqs) + inflight
+        if running_bs >= self.max_running_requests and self.chunked_req is None:
+            return None
+        # slots promised to in-flight prefill batches' future decode growth count as running
+        running_reqs = list(self.running_batch.reqs) + [r for b in self.scheduled_prefill_batches for r in b.reqs]
+        adder = PrefillAdder(self.token_to_kv_pool_allocator.available_size, running_reqs,
+                             self.new_token_ratio, self.max_prefill_tokens, self.chunked_prefill_size)
+        if self.chunked_req is not None:
+            self.chunked_req.init_next_round_input(prefix_len=len(self.chunked_req.fill_ids))
+            self.chunked_req = adder.add_chunked_req(self.chunked_req)
+        rid_set = set(rids)
+        for req in self.waiting_queue:
+            if req.rid not in rid_set:
+                continue
+            if running_bs + len(adder.can_run_list) >= self.max_running_requests:
+                break
+            req.init_next_round_input(prefix_len=0)
+            res = adder.add_one_req(req, self.chunked_req is not None)
+            if res != AddReqResult.CONTINUE:
+                break
+        can_run_list = adder.can_run_list
+        if not can_run_list:
+            return None
+        run = set(id(r) for r in can_run_list)
+        self.waiting_queue = [r for r in self.waiting_queue if id(r) not in run]
+        if adder.new_chunked_req is not None:
+            assert self.chunked_req is None
+            self.chunked_req = adder.new_chunked_req
+        if self.chunked_req:
+            self.chunked_req.is_chunked += 1
+        new_batch = ScheduleBatch.init_new(can_run_list, self.req_to_token_pool,
+                                           self.token_to_kv_pool_allocator, self.device)
+        new_batch.prepare_for_extend()
+        # the request (if any) whose prefill is NOT complete after this batch
+        new_batch.chunked_req = self.chunked_req
+        self.scheduled_prefill_batches.append(new_batch)
+        return new_batch
+
+    def get_next_prefill_batch(self, recv_req: GetNextPrefillBatchInput):
+        batch = self.get_new_batch_prefill(recv_req.rids)
+        if batch is None:
+            return
+        ev = torch.cuda.Event()
+        ev.record(self.stream)  # req_to_token rows of this batch are written before this point
+        self.bridge_socket.put(GetNextPrefillBatchOutput(
+            rids=[r.rid for r in batch.reqs],
+            chunked_rid=(self.chunked_req.rid if self.chunked_req else None),
+            req_pool_indices=[r.req_pool_idx for r in batch.reqs],
+            prefix_lens=[len(r.prefix_indices) for r in batch.reqs],
+            extend_input_lens=[r.extend_input_len for r in batch.reqs],
+            ready_event=ev))
+
+    def process_prefill_result(self, recv_req: BatchProcessPrefillResultReq):
+        batch = self.scheduled_prefill_batches.popleft()  # FIFO: P executes in the order D issued
+        assert len(batch.reqs) == len(recv_req.next_token_ids)
+        if recv_req.done_event is not None:
+            self.stream.wait_event(recv_req.done_event)  # KV rows of the batch precede our decode
+        now = time.perf_counter()
+        keep = []
+        on_device = isinstance(recv_req.next_token_ids, torch.Tensor)
+        host_ids = [-1] * len(batch.reqs) if on_device else recv_req.next_token_ids
+        for i, (req, tok) in enumerate(zip(batch.reqs, host_ids)):
+            if req is batch.chunked_req:
+                continue  # intermediate chunk: the sampled token is discarded
+            req.output_ids.append(int(tok))
+            req.launched_tokens = 1
+            req.first_token_time = now
+            req.token_times.append(now)
+            req.check_finished()
+            if self.token_callback:
+                self.token_callback(req, int(tok), req.finished())
+            if req.finished():
+                self._release(req)
+            else:
+                keep.append(i)
+        if not keep:
+            return
+        if on_device:
+            batch.output_ids = (recv_req.next_token_ids if len(keep) == len(batch.reqs) else
+                                recv_req.next_token_ids[torch.tensor(keep, device=self.device)])
+        else:
+            batch.output_ids = torch.tensor([host_ids[i] for i in keep], dtype=torch.int64,
+                                            pin_memory=True).to(self.device, non_blocking=True)
+        if len(keep) != len(batch.reqs):
+            batch.output_ids, out = None, batch.output_ids
+            batch.filter_batch(keep_indices=keep)
+            batch.output_ids = out
+        self.running_batch.merge_batch(batch)
+
+    # ---- decode ----------------------------------------------------------------------------------
+    def _release(self, req: Req):
+        """Free the KV slots and the request slot (ChunkCache.cache_finished_req,
+        mem_cache/chunk_cache.py:37-42)."""
+        n = len(req.origin_input_ids) + max(req.launched_tokens - 1, 0)
+        slots = self.req_to_token_pool.req_to_token[req.req_pool_idx, :n]
+        self.token_to_kv_pool_allocator.free(slots.long())
+        self.req_to_token_pool.free(req.req_pool_idx)
+        req.finish_time = time.perf_counter()
+        self.num_finished += 1
+        self.finished.put(req)
+
+    def update_running_batch(self, batch: ScheduleBatch) -> ScheduleBatch:
+        # requests whose last token has already been LAUNCHED need no further step
+        keep = [i for i, r in enumerate(batch.reqs)
+                if not r.finished() and r.launched_tokens < r.sampling_params.max_new_tokens]
+        if len(keep) != len(batch.reqs):
+            batch.filter_batch(keep_indices=keep)
+        if batch.is_empty():
+            return batch
+        if not batch.check_decode_mem():
+            torch.cuda.current_stream().synchronize()  # in-flight steps still read the victims' KV
+            self._drain_results(all_of_them=True)
+            old = self.new_token_ratio
+            retracted = batch.retract_decode(RETRACT_DECODE_STEPS)
+            self.new_token_ratio = min(old + 0.1, 1.0)
+            logger.info("Decode out of memory happened. #retracted_reqs: %d, #new_token_ratio: %.4f -> %.4f",
+                        len(retracted), old, self.new_token_ratio)
+            for req in retracted:
+                # re-submit prompt + generated tokens as a fresh prefill (decode_scheduler.py:117-139)
+                msg = TokenizedGenerateReqInput(rid=req.rid, input_text="",
+                                                input_ids=req.origin_input_ids + req.output_ids,
+                                                sampling_params=SamplingParams(
+                                                    max_new_tokens=req.sampling_params.max_new_tokens - len(req.output_ids),
+                                                    ignore_eos=req.sampling_params.ignore_eos),
+                                                is_retracted=True, arrival_time=req.arrival_time)
+                new_req = self.handle_generate_request(msg)
+                new_req.retracted_from = req
+                self.send_to_p_instance.put(msg)
+        else:
+            self.new_token_ratio = max(self.new_token_ratio - self.new_token_ratio_decay,
+                                       self.min_new_token_ratio)
+        batch.prepare_for_decode()
+        return batch
+
+    def get_next_batch_to_run(self) -> Optional[ScheduleBatch]:
+        if self.running_batch.is_empty():
+            return None
+        self.running_batch = self.update_running_batch(self.running_batch)
+        return None if self.running_batch.is_empty() else self.running_batch
+
+    def run_batch(self, batch: ScheduleBatch):
+        mwb = batch.get_model_worker_batch()
+        logits_output, next_token_ids = self.tp_worker.forward_batch_generation(mwb)
+        self.forward_ct += 1
+        batch.output_ids = next_token_ids.to(torch.int64)
+        bs = len(batch.reqs)
+        for r in batch.reqs:
+            r.launched_tokens += 1
+        pinned = None
+        if not self.device_resident:
+            pinned = self._pinned_ring[self._ring_i % len(self._pinned_ring)]
+            self._ring_i += 1
+            if bs > pinned.numel():
+                pinned = torch.empty((bs,), dtype=torch.int32, pin_memory=True)
+            pinned[:bs].copy_(next_token_ids, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        self.result_queue.append((list(batch.reqs), pinned, bs, ev))
+        self.decode_steps += 1
+        self.decode_tokens += bs
+
+    def process_batch_result_decode(self, reqs: List[Req], pinned: torch.Tensor, bs: int, ev):
+        ev.synchronize()
+        now = time.perf_counter()
+        ids = pinned[:bs].tolist() if pinned is not None else [-1] * bs
+        for req, tok in zip(reqs, ids):
+            if req.finished():
+                continue
+            req.output_ids.append(tok)
+            req.token_times.append(now)
+            req.check_finished()
+            if self.token_callback:
+                self.token_callback(req, tok, req.finished())
+            if req.finished():
+                self._release(req)
+
+    def _drain_results(self, all_of_them: bool = False, keep: int = 1):
+        while self.result_queue and (all_of_them or len(self.result_queue) > keep):
+            self.process_batch_result_decode(*self.result_queue.popleft())
+
+    def event_loop(self):
+        """Overlap loop: step N is launched before step N-1's tokens are read back."""
+        idle_spins = 0
+        while not self.stop_flag.is_set():
+            self.recv_requests()
+            self.maybe_schedule_prefill()
+            batch = self.get_next_batch_to_run()
+            if batch is not None:
+                self.run_batch(batch)
+                self._drain_results(keep=1)
+                idle_spins = 0
+            else:
+                self._drain_results(all_of_them=True)
+                self.new_token_ratio = self.init_new_token_ratio  # reset when idle (scheduler.py:555)
+                idle_spins += 1
+                if idle_spins > 50:
+                    time.sleep(0.0002)
+        self._drain_results(all_of_them=True)
+
+
+class SemiPDEngine:
+    """`_launch_semi_pd_subprocesses` (entrypoints/engine.py:540-728) for one GPU: builds the D
+    worker (weights + pools + CUDA graphs), the P worker (adopts D's parameters through the
+    get_ipc_info / share_params_from_ipc call pair), the SM partition, and runs both loops."""
+
+    def __init__(self, server_args: ServerArgs, gpu_id: int = 0, tp_rank: int = 0,
+                 model_config: Optional[ModelConfig] = None, prefill_sm_percent: Optional[int] = None,
+                 decode_sm_percent: Optional[int] = None, partition: str = "green"):
+        assert server_args.enable_semi_pd, "SemiPDEngine needs --enable-semi-pd"
+        self.server_args = server_args
+        self.gpu_id = gpu_id
+        torch.cuda.set_device(gpu_id)
+        model_config = model_config or get_model_config(server_args.model_path)
+        p_pct = PREFILL_ENGINE_SM_PERCENTILE if prefill_sm_percent is None else prefill_sm_percent
+        d_pct = DECODE_ENGINE_SM_PERCENTILE if decode_sm_percent is None else decode_sm_percent
+        total = ops.device_sm_count(gpu_id)
+        self.partition = None
+        if partition == "green":
+            # the reference's caps overlap (80 % + 100 %); green contexts are disjoint, so the two
+            # percentages are normalised to a split of the device
+            p_sms = max(8, int(round(total * p_pct / float(p_pct + d_pct) / 8.0)) * 8)
+            p_sms = min(p_sms, total - 8)
+            self.partition = ops.SmPartition(gpu_id, p_sms, total - p_sms)
+            self.p_stream, self.d_stream = self.partition.prefill_stream, self.partition.decode_stream
+            self.p_sms, self.d_sms = self.partition.prefill_sms, self.partition.decode_sms
+        elif partition == "none":
+            # two plain streams sharing all SMs (decode gets the higher priority); for A/B runs
+            self.p_stream = torch.cuda.Stream(device=gpu_id, priority=0)
+            self.d_stream = torch.cuda.Stream(device=gpu_id, priority=-1)
+            self.p_sms = self.d_sms = total
+        else:
+            raise ValueError(partition)
+
+        # D first: owns weights and the KV pool (engine.py:584-627)
+        with torch.cuda.stream(self.d_stream):
+            ops.set_sm_budget(self.d_sms)
+            self.d_worker = TpModelWorker(server_args, gpu_id, tp_rank, instance_role=InstanceRole.DECODE,
+                                          model_config=model_config)
+            ipc_info = self.d_worker.get_ipc_info()
+            self.d_worker.init_attention_backend()
+            self.d_worker.init_cuda_graphs()
+            self.d_stream.synchronize()
+        # then P with bypass_load_weight=True (engine.py:629-661)
+        with torch.cuda.stream(self.p_stream):
+            ops.set_sm_budget(self.p_sms)
+            self.p_worker = TpModelWorker(server_args, gpu_id, tp_rank, bypass_load_weight=True,
+                                          instance_role=InstanceRole.PREFILL, model_config=model_config)
+            self.p_worker.share_params_from_ipc(ipc_info)
+            self.p_worker.init_attention_backend()
+        ops.set_sm_budget(0)
+        self.max_total_num_tokens = self.d_worker.max_total_num_tokens
+
+        self.decode = SemiPDDecodeScheduler(server_args, self.d_worker, self.d_stream, self.d_sms)
+        self.prefill = SemiPDPrefillScheduler(server_args, self.p_worker, self.p_stream, self.p_sms,
+                                              self.decode.inbox)
+        self.decode.send_to_p_instance = self.prefill.inbox
+        self.decode.bridge_socket = self.prefill.bridge_socket
+        self.threads = [threading.Thread(target=self.decode.run, name="semi-pd-decode", daemon=True),
+                        threading.Thread(target=self.prefill.run, name="semi-pd-prefill", daemon=True)]
+        for t in self.threads:
+            t.start()
+        self._rid = 0
+
+    def warmup(self, prompt_len: int = 64, n: int = 2, max_new_tokens: int = 4):
+        """Run a few requests through both workers (module loads, tensor-map cache, allocator)."""
+        vocab = self.d_worker.model_config.vocab_size
+        reqs = [self.submit([(3 + i + j) % vocab for j in range(prompt_len)], max_new_tokens) for i in range(n)]
+        self.wait(len(reqs))
+        return reqs
+
+    def set_device_resident(self, flag: bool):
+        """Only while idle: switches both workers between host-buffer serving and the
+        device-resident arm."""
+        self.decode.device_resident = self.prefill.device_resident = bool(flag)
+
+    def submit(self, input_ids: List[int], max_new_tokens: int, arrival_time: Optional[float] = None,
+               ignore_eos: bool = True, input_ids_device: Optional[torch.Tensor] = None) -> str:
+        """TokenizerManager.generate_request → push to D and P (tokenizer_manager.py:149-160)."""
+        self._rid += 1
+        rid = f"req-{self._rid}"
+        msg = TokenizedGenerateReqInput(rid=rid, input_text="", input_ids=list(input_ids),
+                                        sampling_params=SamplingParams(max_new_tokens=max_new_tokens,
+                                                                       ignore_eos=ignore_eos),
+                                        arrival_time=time.perf_counter() if arrival_time is None else arrival_time,
+                                        input_ids_device=input_ids_device)
+        self.prefill.inbox.put(msg)  # P first so that it knows the rid before D can schedule it
+        self.decode.inbox.put(msg)
+        return rid
+
+    def wait(self, n: int, timeout: float = 600.0) -> List[Req]:
+        out, t0 = [], time.perf_counter()
+        while len(out) < n:
+            self.check_health()
+            try:
+                out.append(self.decode.finished.get(timeout=0.05))
+            except queue.Empty:
+                if time.perf_counter() - t0 > timeout:
+                    raise TimeoutError(f"only {len(out)}/{n} requests finished in {timeout}s")
+        return out
+
+    def check_health(self):
+        for s in (self.decode, self.prefill):
+            if s.error is not None:
+                raise RuntimeError(f"{s.role} scheduler died") from s.error
+
+    def shutdown(self):
+        self.decode.stop_flag.set()
+        self.prefill.stop_flag.set()
+        for t in self.threads:
+            t.join(timeout=10)
+        torch.cuda.synchronize()
+        if self.partition is not None:
+            self.partition.close()
