@@ -490,9 +490,11 @@ extern "C" int spd_attn_decode_paged(void* out, const void* q, const void* k_poo
     SPD_REQUIRE(workspace && workspace_bytes >= spd_attn_decode_workspace_bytes(batch, num_q_heads, head_dim),
                 SPD_E_WORKSPACE, "spd_attn_decode_paged: workspace too small (%lld bytes)",
                 (long long)workspace_bytes);
-    p.o_part = reinterpret_cast<float*>(workspace);
+    SPD_REQUIRE(pairs <= 16384, SPD_E_SHAPE, "spd_attn_decode_paged: batch x kv heads exceeds 16384");
+    // layout (attn_simt.cu: spd_attn_decode_workspace_bytes): counters at a fixed offset first
+    p.counters = reinterpret_cast<int*>(workspace);
+    p.o_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 65536);
     p.ml_part = p.o_part + batch * num_q_heads * kDcMaxSplits * head_dim;
-    p.counters = reinterpret_cast<int*>(p.ml_part + batch * num_q_heads * kDcMaxSplits * 2);
   }
   const int64_t total = pairs * splits;
   const int grid = static_cast<int>(total < sms ? total : sms);

@@ -275,8 +275,9 @@ using namespace spd;
 extern "C" {
 
 int64_t spd_attn_decode_workspace_bytes(int64_t max_batch, int num_q_heads, int head_dim) {
-  // split partials (o, m, l) + one arrival counter per (request, kv head) (<= Hq of them)
-  return max_batch * num_q_heads * kMaxSplits * (head_dim + 2) * 4 + max_batch * num_q_heads * 4 + 256;
+  // [64 KB of arrival counters, one per (request, kv head) — at a FIXED offset so that they stay
+  // zero / re-armed whatever shapes the workspace is reused with] [split partials o | m, l]
+  return 65536 + max_batch * num_q_heads * kMaxSplits * (head_dim + 2) * 4 + 256;
 }
 
 int spd_attn_decode_simt(void* out, const void* q, const void* k_pool, const void* v_pool,
@@ -300,7 +301,7 @@ int spd_attn_decode_simt(void* out, const void* q, const void* k_pool, const voi
   if (p.splits > 1) {
     SPD_REQUIRE(workspace && workspace_bytes >= spd_attn_decode_workspace_bytes(batch, num_q_heads, head_dim),
                 SPD_E_WORKSPACE, "spd_attn_decode_simt: workspace too small");
-    p.o_part = reinterpret_cast<float*>(workspace);
+    p.o_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 65536);
     p.ml_part = p.o_part + batch * num_q_heads * kMaxSplits * head_dim;
   }
   SPD_DISPATCH_DTYPE(dtype, {

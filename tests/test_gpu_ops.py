@@ -31,11 +31,13 @@ def test_rmsnorm(ops, dtype, bs, hid):
     torch.manual_seed(0)
     x, w, r = torch.randn(bs, hid).to(dtype), torch.randn(hid).to(dtype), torch.randn(bs, hid).to(dtype)
     y = ops.rmsnorm(x.to(DEV), w.to(DEV), 1e-6).cpu()
-    torch.testing.assert_close(y, O.rmsnorm(x, w, 1e-6), rtol=1e-3, atol=_tol(dtype, 1e-3, 8e-3))
+    # bf16: one ulp (2^-8 relative) when the fp32 value sits on a rounding boundary
+    rt = _tol(dtype, 1e-3, 8e-3)
+    torch.testing.assert_close(y, O.rmsnorm(x, w, 1e-6), rtol=rt, atol=_tol(dtype, 1e-3, 8e-3))
     xg, rg = x.to(DEV).clone(), r.to(DEV).clone()
     ops.fused_add_rmsnorm(xg, rg, w.to(DEV), 1e-6)
     ox, orr = O.rmsnorm(x, w, 1e-6, r)
-    torch.testing.assert_close(xg.cpu(), ox, rtol=1e-3, atol=_tol(dtype, 1e-3, 8e-3))
+    torch.testing.assert_close(xg.cpu(), ox, rtol=rt, atol=_tol(dtype, 1e-3, 8e-3))
     assert torch.equal(rg.cpu(), orr)  # residual_out = (x + residual).to(dtype): exact
 
 
@@ -213,7 +215,7 @@ def test_attn_decode(ops, impl, dtype, Hq, Hk, lens):
     out = ops.attn_decode(q.to(DEV).view(len(lens), -1), kp.to(DEV), vp.to(DEV), rtt.to(DEV), rpi.to(DEV),
                           torch.tensor(lens, dtype=torch.int64, device=DEV), Hq, Hk, D, D ** -0.5, impl=impl)
     err = (out.cpu().float().view(-1, Hq, D) - ref.float()).abs().max().item()
-    assert err < _tol(dtype, 2e-3, 1e-2), err
+    assert err < _tol(dtype, 2e-3, 1.6e-2), err  # bf16: one output ulp at |o| < 4
 
 
 @pytest.mark.parametrize("impl", ["tc", "simt"])
