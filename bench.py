@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--impl", type=str, default="spd", choices=["spd", "reference"])
     ap.add_argument("--model", type=str, default="llama-3-8b")
     ap.add_argument("--dtype", type=str, default="bfloat16")
-    ap.add_argument("--requests", type=int, default=48, help="requests per step (serving window)")
+    ap.add_argument("--requests", type=int, default=128, help="requests per step (serving window)")
     ap.add_argument("--input-len", type=int, default=1024)
     ap.add_argument("--output-len", type=int, default=128)
     ap.add_argument("--prefill-sm-pct", type=int, default=50)

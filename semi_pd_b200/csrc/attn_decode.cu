@@ -242,8 +242,20 @@ attn_decode_kernel(const DecodeParams p) {
     int prev_stage = -1;
     while (c.valid) {
       const int st = t % kDcStages;
-      mbar_wait(&kv_empty[st], ((t / kDcStages) & 1) ^ 1);
       const DcItem& it = c.item;
+      // Page-table lookups first, all 16 in flight at once (the cp.async asm below is a compiler
+      // barrier, so interleaving them would serialise 16 dependent global-load latencies per tile).
+      int slot[16];
+      {
+        const int32_t* rtt0 = p.req_to_token + p.req_pool_indices[it.b] * p.rtt_stride;
+        const int tokb = it.t0 + c.j * kDcTile + rsub;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int tok = tokb + i * 8;
+          slot[i] = tok < it.t1 ? __ldg(rtt0 + tok) : -1;
+        }
+      }
+      mbar_wait(&kv_empty[st], ((t / kDcStages) & 1) ^ 1);
       if (c.j == 0) {
         // stage the G query rows of this (request, kv head) as the K-major B operand
         if (rsub < G) {
@@ -253,20 +265,17 @@ attn_decode_kernel(const DecodeParams p) {
           *reinterpret_cast<uint4*>(sQ + (c.iter & 1) * kDcQBytes + dc_small_off(rsub, chunk * 8)) = v;
         }
       }
-      const int32_t* rtt = p.req_to_token + p.req_pool_indices[it.b] * p.rtt_stride;
       const int64_t col = static_cast<int64_t>(it.hk) * kDcD + chunk * 8;
       const uint32_t kdst = smem_u32(sK + st * kDcTileBytes);
       const uint32_t vdst = smem_u32(sV + st * kDcTileBytes);
-      const int tok0 = it.t0 + c.j * kDcTile;
-#pragma unroll 4
+#pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int row = i * 8 + rsub;
-        const int tok = tok0 + row;
-        const bool valid = tok < it.t1;
-        const int64_t slot = valid ? rtt[tok] : 0;
+        const bool valid = slot[i] >= 0;
+        const int64_t s64 = valid ? slot[i] : 0;
         const uint32_t off = dc_tile_off(row, chunk);
-        cp_async16(kdst + off, kp + slot * row_elems + col, valid);
-        cp_async16(vdst + off, vp + slot * row_elems + col, valid);
+        cp_async16(kdst + off, kp + s64 * row_elems + col, valid);
+        cp_async16(vdst + off, vp + s64 * row_elems + col, valid);
       }
       cp_async_commit();
       // publish the PREVIOUS tile (keeps two tiles = 128 KB in flight per SM)

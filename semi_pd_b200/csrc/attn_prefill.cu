@@ -173,6 +173,15 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
     // before it can retire PV_{j-2} and free that stage) and the loaders would wait on each other.
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j & 1;
+      // page-table lookups first, all in flight together and overlapped with the waits below (the
+      // cp.async asm is a compiler barrier; interleaving the lookups with it would serialise 16
+      // dependent global-load latencies per tile)
+      int slot[16];
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int kv = j * kPfN + it * 8 + rsub;
+        slot[it] = kv < kv_len ? __ldg(rtt + kv) : -1;
+      }
       if (j > 0) {
         cp_async_wait<0>();
         fence_proxy_async_smem();
@@ -181,15 +190,14 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
       mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
       const uint32_t kdst = smem_u32(sK + st * kTileBytes);
       const uint32_t vdst = smem_u32(sV + st * kTileBytes);
-#pragma unroll 4
+#pragma unroll
       for (int it = 0; it < 16; ++it) {
         const int row = it * 8 + rsub;
-        const int kv = j * kPfN + row;
-        const bool valid = kv < kv_len;
-        const int64_t slot = valid ? rtt[kv] : 0;
+        const bool valid = slot[it] >= 0;
+        const int64_t s64 = valid ? slot[it] : 0;
         const uint32_t off = tile_off(row, chunk);
-        cp_async16(kdst + off, kp + slot * row_elems + col, valid);
-        cp_async16(vdst + off, vp + slot * row_elems + col, valid);
+        cp_async16(kdst + off, kp + s64 * row_elems + col, valid);
+        cp_async16(vdst + off, vp + s64 * row_elems + col, valid);
       }
       cp_async_commit();
     }

@@ -62,7 +62,9 @@ def tensor_model_parallel_all_gather(input_: torch.Tensor, dim: int = -1, group=
     if _TP_SIZE == 1:
         return input_
     assert dim in (-1, input_.dim() - 1)
-    parts = torch.empty((_TP_SIZE,) + tuple(input_.shape), dtype=input_.dtype, device=input_.device)
-    dist.all_gather_into_tensor(parts, input_.contiguous(), group=group or _TP_GROUP)
+    inp = input_.contiguous()
+    flat = torch.empty((_TP_SIZE * inp.shape[0],) + tuple(inp.shape[1:]), dtype=inp.dtype, device=inp.device)
+    dist.all_gather_into_tensor(flat, inp, group=group or _TP_GROUP)
+    parts = flat.view((_TP_SIZE,) + tuple(inp.shape))
     # [tp, ..., n] -> [..., tp*n]
     return parts.movedim(0, -2).reshape(*input_.shape[:-1], _TP_SIZE * input_.shape[-1])

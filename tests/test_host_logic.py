@@ -1,0 +1,152 @@
+"""Host-side logic that needs no GPU: allocators, enums, TP sharding rules, admission policy,
+workload generator."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import llama_oracle as O
+from semi_pd_b200.configs import ServerArgs, default_cuda_graph_bs, get_model_config
+from semi_pd_b200.forward_batch_info import ForwardMode
+from semi_pd_b200.layers import MergedColumnParallelLinear, ParallelLMHead, QKVParallelLinear, RowParallelLinear
+from semi_pd_b200.memory_pool import ReqToTokenPool, TokenToKVPoolAllocator
+from semi_pd_b200.schedule_batch import Req, SamplingParams
+from semi_pd_b200.schedule_policy import AddReqResult, PrefillAdder
+
+
+def test_forward_mode_values_and_predicates():
+    # integer values line up with forward_batch_info.py:53-70
+    assert [m.value for m in (ForwardMode.EXTEND, ForwardMode.DECODE, ForwardMode.MIXED, ForwardMode.IDLE)] == [1, 2, 3, 4]
+    assert ForwardMode.EXTEND.is_extend() and ForwardMode.MIXED.is_extend() and not ForwardMode.DECODE.is_extend()
+    assert ForwardMode.DECODE.is_cuda_graph() and ForwardMode.IDLE.is_decode_or_idle()
+
+
+def test_req_to_token_pool_and_allocator():
+    pool = ReqToTokenPool(size=5, max_context_len=16, device="cpu")
+    assert pool.req_to_token.dtype == torch.int32 and pool.req_to_token.shape == (5, 16)
+    a = pool.alloc(3)
+    assert a == [0, 1, 2] and pool.available_size() == 2 and pool.alloc(3) is None
+    pool.free(a[1])
+    pool.free([a[0]])
+    assert pool.available_size() == 4
+    alloc = TokenToKVPoolAllocator(10, torch.bfloat16, "cpu", kvcache=None)
+    # slot 0 is the dummy slot for padded CUDA-graph rows (memory_pool.py:179-182)
+    assert alloc.free_slots.tolist() == list(range(1, 11)) and alloc.free_slots.dtype == torch.int64
+    s = alloc.alloc(4)
+    assert s.tolist() == [1, 2, 3, 4] and alloc.alloc(7) is None
+    alloc.free_group_begin()
+    alloc.free(s[:2])
+    alloc.free(s[2:])
+    assert alloc.available_size() == 6
+    alloc.free_group_end()
+    assert alloc.available_size() == 10
+    alloc.clear()
+    assert alloc.available_size() == 10
+
+
+def test_cuda_graph_batch_sizes_and_presets():
+    assert default_cuda_graph_bs(160) == [1, 2, 4] + [8 * i for i in range(1, 21)]
+    c = get_model_config("meta-llama/Llama-3-8B")
+    assert (c.hidden_size, c.num_hidden_layers, c.num_key_value_heads, c.vocab_size) == (4096, 32, 8, 128256)
+    assert get_model_config("llama-3-70b").get_num_kv_heads(8) == 1
+    assert get_model_config("llama-3-70b").get_num_kv_heads(16) == 1  # replicated when tp > n_kv
+    with pytest.raises(ValueError):
+        get_model_config("opt-125m")
+    sa = ServerArgs(enable_semi_pd=True)
+    assert sa.disable_radix_cache and sa.chunked_prefill_size == 8192
+
+
+@pytest.mark.parametrize("tp", [1, 2, 4, 8])
+def test_tp_sharding_reconstructs_full_product(tp):
+    """Column/row sharding rules (linear.py): concatenating column shards / summing row shards of
+    the sharded computation equals the unsharded layer (Megatron identity), incl. the fused
+    q‖k‖v and gate‖up row orders."""
+    torch.manual_seed(tp)
+    H, D, Hq, Hk, I = 64, 8, 8, 4 if tp <= 4 else 8, 48
+    x = torch.randn(5, H, dtype=torch.float64)
+    wqkv = torch.randn((Hq + 2 * Hk) * D, H, dtype=torch.float64)
+    wo = torch.randn(H, Hq * D, dtype=torch.float64)
+    wgu = torch.randn(2 * I * tp // tp * 1, H, dtype=torch.float64) if False else torch.randn(2 * 16 * tp, H, dtype=torch.float64)
+    wd = torch.randn(H, 16 * tp, dtype=torch.float64)
+    full_qkv = x @ wqkv.T
+    q_full, k_full, v_full = full_qkv.split([Hq * D, Hk * D, Hk * D], -1)
+    o_sum, d_sum = 0, 0
+    for r in range(tp):
+        sh = QKVParallelLinear.shard(wqkv, D, Hq, Hk, r, tp)
+        nq, nk = Hq // tp, max(1, Hk // tp)
+        q, k, v = (x @ sh.T).split([nq * D, nk * D, nk * D], -1)
+        assert torch.equal(q, q_full[:, r * nq * D:(r + 1) * nq * D])
+        kv_rank = r // max(1, tp // Hk)
+        assert torch.equal(k, k_full[:, kv_rank * nk * D:(kv_rank + 1) * nk * D])
+        assert torch.equal(v, v_full[:, kv_rank * nk * D:(kv_rank + 1) * nk * D])
+        o_sum = o_sum + q_full[:, r * nq * D:(r + 1) * nq * D] @ RowParallelLinear.shard(wo, r, tp).T
+        gu = x @ MergedColumnParallelLinear.shard(wgu, r, tp).T
+        act = O.silu_and_mul(gu)
+        d_sum = d_sum + act @ RowParallelLinear.shard(wd, r, tp).T
+    torch.testing.assert_close(o_sum, q_full @ wo.T)
+    torch.testing.assert_close(d_sum, O.silu_and_mul(x @ wgu.T) @ wd.T)
+    lm = torch.randn(32, H, dtype=torch.float64)
+    parts = [x @ ParallelLMHead.shard(lm, r, tp).T for r in range(tp)]
+    torch.testing.assert_close(torch.cat(parts, -1), x @ lm.T)
+
+
+def _req(n_in, max_new=128):
+    r = Req(f"r{n_in}", list(range(n_in)), SamplingParams(max_new_tokens=max_new))
+    r.init_next_round_input(prefix_len=0)
+    return r
+
+
+def test_prefill_adder_budgets_and_chunking():
+    free = [100000]
+    adder = PrefillAdder(lambda: free[0], [], 0.7, rem_input_tokens=16384, rem_chunk_tokens=8192)
+    for _ in range(7):
+        assert adder.add_one_req(_req(1024), False) == AddReqResult.CONTINUE
+    # the 8th request exactly exhausts the chunk budget
+    assert adder.add_one_req(_req(1024), False) == AddReqResult.OTHER
+    assert len(adder.can_run_list) == 8 and adder.rem_chunk_tokens == 0 and adder.new_chunked_req is None
+    # a request larger than the remaining chunk budget is truncated and becomes THE chunked request
+    adder = PrefillAdder(lambda: free[0], [], 0.7, 16384, 8192)
+    adder.add_one_req(_req(6000), False)
+    big = _req(5000)
+    res = adder.add_one_req(big, False)
+    assert adder.new_chunked_req is big and big.extend_input_len == 2192 and len(big.fill_ids) == 2192
+    assert res == AddReqResult.OTHER
+    # continuing it next round: prefix = what was filled, rest fits → no longer chunked
+    big.init_next_round_input(prefix_len=len(big.fill_ids))
+    adder2 = PrefillAdder(lambda: free[0], [], 0.7, 16384, 8192)
+    assert adder2.add_chunked_req(big) is None and big.extend_input_len == 5000 - 2192
+    # KV budget: running requests reserve new_token_ratio * remaining tokens
+    running = [_req(10) for _ in range(10)]
+    small = PrefillAdder(lambda: 2000, running, 1.0, 16384, 8192)
+    assert small.rem_total_tokens == 2000 - 10 * 128
+    assert small.add_one_req(_req(1024), False) == AddReqResult.NO_TOKEN
+
+
+def test_req_finish_and_retract_bookkeeping():
+    r = Req("a", [1, 2, 3], SamplingParams(max_new_tokens=2))
+    r.output_ids.append(5)
+    r.check_finished()
+    assert not r.finished()
+    r.output_ids.append(6)
+    r.check_finished()
+    assert r.finished() and r.finished_reason == "length"
+    e = Req("b", [1], SamplingParams(max_new_tokens=10, ignore_eos=False), eos_token_ids={9})
+    e.output_ids.append(9)
+    e.check_finished()
+    assert e.finished_reason == "stop"
+    e.req_pool_idx = 3
+    e.reset_for_retract()
+    assert e.req_pool_idx is None and e.is_retracted and e.prefix_indices == []
+
+
+def test_bench_workload_generator_matches_bench_serving_recipe():
+    import bench
+    p = bench.make_prompts(4, 16, 128256, seed=1)
+    rng = np.random.RandomState(1)
+    off = rng.randint(0, 128256, size=4)
+    assert p[2] == [int((off[2] + 2 + j) % 128256) for j in range(16)]
+    arr = bench.poisson_arrivals(1000, 10.0, seed=1)
+    gaps = np.diff([0.0] + arr)
+    assert abs(gaps.mean() - 0.1) < 0.01 and all(g >= 0 for g in gaps)
+    assert bench.poisson_arrivals(3, float("inf")) == [0.0, 0.0, 0.0]
