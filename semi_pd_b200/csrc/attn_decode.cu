@@ -14,12 +14,17 @@
 // grid = #SMs (or the partition's SM budget); each CTA walks work items (request, kv head,
 // kv split) with a static stride and keeps its TMEM, barriers and the 3-stage K/V ring alive
 // across items, so the gather of the next item overlaps the epilogue of the current one.
-// Splits are merged by the last-arriving CTA of a (request, kv head) pair — no host plan, no
-// second launch, CUDA-graph safe (counters re-arm themselves).
+// Splits (only used when request x kv-head pairs do not fill the SMs) are merged by the
+// last-arriving CTA of a pair — no host plan, no second launch, CUDA-graph safe.
 //
-// warps 0-3: softmax over TMEM lanes (column reductions via shuffles + smem), O rescale, epilogue
-// warps 4-7: K/V gather through req_to_token (16-byte cp.async, 128-byte swizzle), Q staging
-// warp  8  : MMA issuer + TMEM allocator
+// Softmax without per-tile reductions: every thread owns one kv token of the tile (a TMEM lane of
+// S^T).  All threads exponentiate against a shared REFERENCE max m_ref that is only raised when
+// some score exceeds it by more than 2^8 (one barrier-with-OR per tile detects that); row sums are
+// kept per thread and reduced once per item.  Raising m_ref (always on an item's first tile,
+// rarely afterwards) takes the slow path: true tile max via shuffles, O^T rescaled in TMEM.
+//
+// warps 0-3: softmax, O rescale, epilogue     warps 4-7: K/V gather through req_to_token (16-byte
+// cp.async, 128-byte swizzle) + Q staging     warp 8: MMA issuer + TMEM allocator
 #include <cuda.h>
 
 #include "common.cuh"
@@ -34,9 +39,12 @@ constexpr int kDcN = 16;       // UMMA N (>= GQA group)
 constexpr int kDcStages = 3;
 constexpr int kDcTileBytes = 128 * 128 * 2;
 constexpr int kDcQBytes = 16 * 128 * 2;   // [16 rows x 128 d] as two 2 KB swizzle blocks
-constexpr int kDcSmem = kDcStages * 2 * kDcTileBytes + 2 * kDcQBytes + 2 * kDcQBytes + 1024 + 1024;
+constexpr int kDcLenCache = 1024;         // seq_lens cached in smem
+constexpr int kDcMisc = 1024 + kDcLenCache * 4;
+constexpr int kDcSmem = kDcStages * 2 * kDcTileBytes + 4 * kDcQBytes + 1024 + kDcMisc;
 constexpr int kDcMaxSplits = 32;
 constexpr int kDcMaxGroup = 8;
+constexpr float kDcRescale = 8.0f;  // log2 units a score may exceed m_ref before it is raised
 
 struct DecodeParams {
   void* out;
@@ -58,13 +66,13 @@ struct DcItem {
   int b, hk, split, t0, t1, n_tiles;
 };
 
-__device__ __forceinline__ DcItem dc_item(const DecodeParams& p, int w) {
+__device__ __forceinline__ DcItem dc_item(const DecodeParams& p, const int* s_len, int w) {
   DcItem it;
   it.split = w % p.splits;
   const int r = w / p.splits;
   it.hk = r % p.Hk;
   it.b = r / p.Hk;
-  const int L = static_cast<int>(p.seq_lens[it.b]);
+  const int L = it.b < kDcLenCache ? s_len[it.b] : static_cast<int>(p.seq_lens[it.b]);
   int per = (L + p.splits - 1) / p.splits;
   per = (per + kDcTile - 1) / kDcTile * kDcTile;
   it.t0 = it.split * per;
@@ -79,26 +87,26 @@ struct DcCursor {
   int w, iter, j;
   DcItem item;
   bool valid;
-  __device__ __forceinline__ void init(const DecodeParams& p, int total) {
+  __device__ __forceinline__ void init(const DecodeParams& p, const int* s_len, int total) {
     w = blockIdx.x;
     iter = 0;
     j = 0;
-    settle(p, total);
+    settle(p, s_len, total);
   }
-  __device__ __forceinline__ void settle(const DecodeParams& p, int total) {
+  __device__ __forceinline__ void settle(const DecodeParams& p, const int* s_len, int total) {
     valid = false;
     while (w < total) {
-      item = dc_item(p, w);
+      item = dc_item(p, s_len, w);
       if (item.n_tiles > 0) { valid = true; return; }
       w += gridDim.x;  // empty items carry no tiles (the softmax warps still publish them)
     }
   }
-  __device__ __forceinline__ void next(const DecodeParams& p, int total) {
+  __device__ __forceinline__ void next(const DecodeParams& p, const int* s_len, int total) {
     if (++j >= item.n_tiles) {
       j = 0;
       w += gridDim.x;
       ++iter;
-      settle(p, total);
+      settle(p, s_len, total);
     }
   }
 };
@@ -111,6 +119,20 @@ __device__ __forceinline__ uint32_t dc_small_off(int row, int col) {
   const int chunk = col >> 3;
   return (chunk >> 3) * 2048 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4) + (col & 7) * 2;
 }
+// barrier + OR-reduction over the 128 softmax threads (named barrier 1)
+__device__ __forceinline__ bool softmax_bar_or(bool pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %1, 0;\n\t"
+      "barrier.cta.red.or.pred p, 1, 128, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(out)
+      : "r"(static_cast<uint32_t>(pred))
+      : "memory");
+  return out != 0;
+}
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <typename T>
 __global__ void __launch_bounds__(kDcThreads, 1)
@@ -134,7 +156,8 @@ attn_decode_kernel(const DecodeParams p) {
   uint64_t* o_empty = bars + 15;   // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
   int* flag_slot = reinterpret_cast<int*>(tmem_slot + 1);
-  float* red = reinterpret_cast<float*>(misc + 256);  // [2 parity][2 (max,sum)][4 warps][8 heads]
+  float* red = reinterpret_cast<float*>(misc + 256);   // [4 warps][8 heads] scratch (+ 8 totals)
+  int* s_len = reinterpret_cast<int*>(misc + 1024);    // seq_lens[0 .. kDcLenCache)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -150,7 +173,7 @@ attn_decode_kernel(const DecodeParams p) {
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
         mbar_init(&s_empty[i], 4);
-        mbar_init(&p_full[i], 4);
+        mbar_init(&p_full[i], 128);
         mbar_init(&p_empty[i], 1);
         mbar_init(&o_empty[i], 4);
       }
@@ -165,6 +188,11 @@ attn_decode_kernel(const DecodeParams p) {
   for (int i = threadIdx.x; i < (4 * kDcQBytes) / 16; i += kDcThreads)
     reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
+
+  // everything above overlaps the previous kernel's tail under PDL; seq_lens is its output
+  griddep_wait();
+  for (int i = threadIdx.x; i < min(p.batch, kDcLenCache); i += kDcThreads)
+    s_len[i] = static_cast<int>(p.seq_lens[i]);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -172,16 +200,14 @@ attn_decode_kernel(const DecodeParams p) {
   const uint32_t tmem_S = tmem_base;        // 2 x 16 columns
   const uint32_t tmem_O = tmem_base + 32;   // 2 x 16 columns
 
-  griddep_wait();
-
   if (warp == 8) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc<T>(128, kDcN, 0, 0);  // A = K (K-major), B = Q (K-major)
       constexpr uint32_t idesc_o = umma_idesc<T>(128, kDcN, 1, 0);  // A = V (MN-major), B = P^T (K-major)
       DcCursor cs, cp;  // cs runs one tile ahead of cp
-      cs.init(p, total);
-      cp.init(p, total);
+      cs.init(p, s_len, total);
+      cp.init(p, s_len, total);
       int ts = 0;  // global tile counter of the S stream
       auto issue_s = [&]() {
         const int st = ts % kDcStages, sb = ts & 1;
@@ -199,7 +225,7 @@ attn_decode_kernel(const DecodeParams p) {
         }
         umma_commit(&s_full[sb]);
         ++ts;
-        cs.next(p, total);
+        cs.next(p, s_len, total);
       };
       if (cs.valid) issue_s();
       int tp = 0;  // global tile counter of the PV stream
@@ -225,7 +251,7 @@ attn_decode_kernel(const DecodeParams p) {
         umma_commit(&p_empty[pb]);
         umma_commit(o_done);
         ++tp;
-        cp.next(p, total);
+        cp.next(p, s_len, total);
       }
     }
   } else if (warp >= 4) {
@@ -237,7 +263,7 @@ attn_decode_kernel(const DecodeParams p) {
     const T* vp = reinterpret_cast<const T*>(p.v_pool);
     const int64_t row_elems = static_cast<int64_t>(p.Hk) * kDcD;
     DcCursor c;
-    c.init(p, total);
+    c.init(p, s_len, total);
     int t = 0;
     int prev_stage = -1;
     while (c.valid) {
@@ -286,7 +312,7 @@ attn_decode_kernel(const DecodeParams p) {
       }
       prev_stage = st;
       ++t;
-      c.next(p, total);
+      c.next(p, s_len, total);
     }
     if (prev_stage >= 0) {
       cp_async_wait<0>();
@@ -297,13 +323,13 @@ attn_decode_kernel(const DecodeParams p) {
     // ===================== softmax / correction / epilogue =====================
     const int tid = threadIdx.x;  // TMEM lane: kv token within tile (S^T) or head-dim index (O^T)
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    int t = 0;  // global tile counter
+    int t = 0;     // global tile counter
     int iter = 0;  // non-empty items seen so far (same convention as DcCursor::iter)
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
-      const DcItem it = dc_item(p, w);
-      float m_run[kDcMaxGroup], l_run[kDcMaxGroup];
+      const DcItem it = dc_item(p, s_len, w);
+      float m_ref[kDcMaxGroup], l_thr[kDcMaxGroup];
 #pragma unroll
-      for (int g = 0; g < kDcMaxGroup; ++g) { m_run[g] = -INFINITY; l_run[g] = 0.f; }
+      for (int g = 0; g < kDcMaxGroup; ++g) { m_ref[g] = -INFINITY; l_thr[g] = 0.f; }
       const int ob = iter & 1;
       for (int j = 0; j < it.n_tiles; ++j, ++t) {
         const int sb = t & 1;
@@ -317,40 +343,33 @@ attn_decode_kernel(const DecodeParams p) {
         if (lane == 0) mbar_arrive(&s_empty[sb]);
         const bool valid = (it.t0 + j * kDcTile + tid) < it.t1;
         float s[kDcMaxGroup];
-        float* rmax = red + (t & 1) * 64;
-        float* rsum = rmax + 32;
+        bool exceed = false;
 #pragma unroll
         for (int g = 0; g < kDcMaxGroup; ++g) {
           s[g] = valid ? __uint_as_float(r[g]) * p.scale_log2 : -INFINITY;
-          const float wm = warp_max(s[g]);
-          if (lane == 0) rmax[warp * 8 + g] = wm;
+          exceed |= (g < G) && (s[g] > m_ref[g] + kDcRescale);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        float alpha[kDcMaxGroup], pv[kDcMaxGroup];
-        bool any_rescale = false;
+        // one barrier per tile: does ANY score need a higher reference max?
+        if (softmax_bar_or(exceed)) {
+          // slow path (first tile of an item, rarely later): true tile max, raise m_ref, rescale
 #pragma unroll
-        for (int g = 0; g < kDcMaxGroup; ++g) {
-          const float mt = fmaxf(fmaxf(rmax[g], rmax[8 + g]), fmaxf(rmax[16 + g], rmax[24 + g]));
-          const float m_new = fmaxf(m_run[g], mt);  // finite: every tile has >= 1 valid token
-          alpha[g] = (m_run[g] == -INFINITY) ? 0.f : fast_exp2(m_run[g] - m_new);
-          any_rescale |= (g < G) && (alpha[g] != 1.f);
-          m_run[g] = m_new;
-          // round to the operand type first so that l matches what the tensor core multiplies
-          pv[g] = to_f32<T>(from_f32<T>(fast_exp2(s[g] - m_new)));
-          const float ws = warp_sum(pv[g]);
-          if (lane == 0) rsum[warp * 8 + g] = ws;
-        }
-        // P^T -> smem (B operand, K-major: row = head, col = kv token)
-        mbar_wait(&p_empty[sb], ((t >> 1) & 1) ^ 1);
-        uint8_t* pdst = sP + sb * kDcQBytes;
+          for (int g = 0; g < kDcMaxGroup; ++g) {
+            const float wm = warp_max(s[g]);
+            if (lane == 0) red[warp * 8 + g] = wm;
+          }
+          softmax_bar();
+          float alpha[kDcMaxGroup];
 #pragma unroll
-        for (int g = 0; g < kDcMaxGroup; ++g)
-          if (g < G) *reinterpret_cast<T*>(pdst + dc_small_off(g, tid)) = from_f32<T>(pv[g]);
-        // O^T rescale needs PV_{t-1} complete
-        if (j > 0) {
-          mbar_wait(o_done, (t - 1) & 1);
-          tc_fence_after_sync();
-          if (any_rescale) {
+          for (int g = 0; g < kDcMaxGroup; ++g) {
+            const float mt = fmaxf(fmaxf(red[g], red[8 + g]), fmaxf(red[16 + g], red[24 + g]));
+            const float m_new = fmaxf(m_ref[g], mt);  // finite: every tile has >= 1 valid token
+            alpha[g] = (m_ref[g] == -INFINITY) ? 0.f : fast_exp2(m_ref[g] - m_new);
+            l_thr[g] *= alpha[g];
+            m_ref[g] = m_new;
+          }
+          if (j > 0) {
+            mbar_wait(o_done, (t - 1) & 1);  // O^T stable: PV_{t-1} complete
+            tc_fence_after_sync();
             uint32_t o[16];
             tmem_ld_32x32b_x16(tmem_O + lane_base + ob * kDcN, o);
             tmem_ld_wait();
@@ -359,20 +378,35 @@ attn_decode_kernel(const DecodeParams p) {
               o[g] = __float_as_uint(__uint_as_float(o[g]) * alpha[g]);
             tmem_st_32x32b_x16(tmem_O + lane_base + ob * kDcN, o);
             tmem_st_wait();
+            tc_fence_before_sync();
+          }
+          softmax_bar();  // `red` may be reused by the next slow path
+        }
+        // P^T -> smem (B operand, K-major: row = head, col = kv token); row sums stay per thread
+        mbar_wait(&p_empty[sb], ((t >> 1) & 1) ^ 1);
+        uint8_t* pdst = sP + sb * kDcQBytes;
+#pragma unroll
+        for (int g = 0; g < kDcMaxGroup; ++g) {
+          if (g < G) {
+            const T pt = from_f32<T>(fast_exp2(s[g] - m_ref[g]));  // <= 2^8; 0 for invalid rows
+            l_thr[g] += to_f32<T>(pt);  // sum what the tensor core multiplies
+            *reinterpret_cast<T*>(pdst + dc_small_off(g, tid)) = pt;
           }
         }
         fence_proxy_async_smem();
-        tc_fence_before_sync();
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // also publishes rsum
-        if (lane == 0) mbar_arrive(&p_full[sb]);
-#pragma unroll
-        for (int g = 0; g < kDcMaxGroup; ++g) {
-          const float st_ = (rsum[g] + rsum[8 + g]) + (rsum[16 + g] + rsum[24 + g]);
-          l_run[g] = l_run[g] * alpha[g] + st_;
-        }
+        mbar_arrive(&p_full[sb]);  // 128 arrivals
       }
-      // ---- epilogue of this item ----
-      float o[kDcMaxGroup];
+      // ---- epilogue of this item: reduce the per-thread row sums, then O^T / l ----
+#pragma unroll
+      for (int g = 0; g < kDcMaxGroup; ++g) {
+        const float ws = warp_sum(l_thr[g]);
+        if (lane == 0) red[warp * 8 + g] = ws;
+      }
+      softmax_bar();
+      float l_tot[kDcMaxGroup], o[kDcMaxGroup];
+#pragma unroll
+      for (int g = 0; g < kDcMaxGroup; ++g)
+        l_tot[g] = (red[g] + red[8 + g]) + (red[16 + g] + red[24 + g]);
       if (it.n_tiles > 0) {
         mbar_wait(o_done, (t - 1) & 1);
         tc_fence_after_sync();
@@ -394,19 +428,20 @@ attn_decode_kernel(const DecodeParams p) {
                  static_cast<int64_t>(it.hk) * G * kDcD + tid;
 #pragma unroll
         for (int g = 0; g < kDcMaxGroup; ++g)
-          if (g < G) dst[g * kDcD] = from_f32<T>(l_run[g] > 0.f ? o[g] / l_run[g] : 0.f);
+          if (g < G) dst[g * kDcD] = from_f32<T>(l_tot[g] > 0.f ? o[g] / l_tot[g] : 0.f);
+        softmax_bar();  // `red` is rewritten by the next item
       } else {
 #pragma unroll
         for (int g = 0; g < kDcMaxGroup; ++g)
           if (g < G) {
             const int64_t idx = (static_cast<int64_t>(it.b) * p.Hq + it.hk * G + g) * p.splits + it.split;
             p.o_part[idx * kDcD + tid] = o[g];
-            if (tid == 0) { p.ml_part[idx * 2] = m_run[g]; p.ml_part[idx * 2 + 1] = l_run[g]; }
+            if (tid == 0) { p.ml_part[idx * 2] = m_ref[g]; p.ml_part[idx * 2 + 1] = l_tot[g]; }
           }
         __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        softmax_bar();
         if (tid == 0) *flag_slot = atomicAdd(&p.counters[it.b * p.Hk + it.hk], 1);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        softmax_bar();
         if (*flag_slot == p.splits - 1) {
           // last split of this (request, kv head): merge all partials in split order
           __threadfence();
@@ -414,16 +449,17 @@ attn_decode_kernel(const DecodeParams p) {
           for (int g = 0; g < G; ++g) {
             const int64_t base = (static_cast<int64_t>(it.b) * p.Hq + it.hk * G + g) * p.splits;
             float M = -INFINITY;
+#pragma unroll 4
             for (int s2 = 0; s2 < p.splits; ++s2) M = fmaxf(M, __ldcg(&p.ml_part[(base + s2) * 2]));
             float num = 0.f, den = 0.f;
+#pragma unroll 4
             for (int s2 = 0; s2 < p.splits; ++s2) {
               const float mm = __ldcg(&p.ml_part[(base + s2) * 2]);
               const float ll = __ldcg(&p.ml_part[(base + s2) * 2 + 1]);
-              if (ll > 0.f) {
-                const float wgt = fast_exp2(mm - M);
-                num += wgt * __ldcg(&p.o_part[(base + s2) * kDcD + tid]);
-                den += wgt * ll;
-              }
+              const float ov = __ldcg(&p.o_part[(base + s2) * kDcD + tid]);
+              const float wgt = ll > 0.f ? fast_exp2(mm - M) : 0.f;
+              num += wgt * ov;
+              den += wgt * ll;
             }
             reinterpret_cast<T*>(p.out)[it.b * p.out_stride +
                                         (static_cast<int64_t>(it.hk) * G + g) * kDcD + tid] =
@@ -431,7 +467,7 @@ attn_decode_kernel(const DecodeParams p) {
           }
           if (tid == 0) p.counters[it.b * p.Hk + it.hk] = 0;  // re-arm for the next launch
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // flag_slot is reused by the next item
+        softmax_bar();  // flag_slot / red are reused by the next item
       }
     }
   }
@@ -481,18 +517,13 @@ extern "C" int spd_attn_decode_paged(void* out, const void* q, const void* k_poo
   p.out_stride = out_stride;
   p.rtt_stride = req_to_token_stride;
   p.scale_log2 = sm_scale * 1.4426950408889634f;
-  // KV splits: balance equal-sized work items over the persistent CTAs (lengths are device-side,
-  // so the choice depends on the launch shape only — nothing to plan on the host per step)
+  // KV splits only when the (request, kv head) pairs cannot fill the SMs; the choice depends on
+  // the launch shape alone (lengths are device-side) — nothing to plan on the host per step.
   const int64_t pairs = batch * num_kv_heads;
   int splits = 1;
-  {
-    double best = 1e30;
-    for (int s = 1; s <= kDcMaxSplits; ++s) {
-      const int64_t items = pairs * s;
-      const int64_t rounds = (items + sms - 1) / sms;
-      const double cost = static_cast<double>(rounds) / s + 0.02 * (s - 1);
-      if (cost < best - 1e-9) { best = cost; splits = s; }
-    }
+  if (pairs < sms) {
+    splits = static_cast<int>((sms + pairs - 1) / pairs);
+    if (splits > kDcMaxSplits) splits = kDcMaxSplits;
   }
   p.splits = splits;
   if (splits > 1) {

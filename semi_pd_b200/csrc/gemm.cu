@@ -8,8 +8,11 @@
 //     tile list M-fastest so the W tile of a column block is shared through L2.
 //   * decode regime (M <= 256), "swap-AB": D[128 x BN] = W_tile[128 rows of N] * A[BN >= M]^T,
 //     i.e. the weight dimension feeds UMMA-M (128 TMEM lanes) and the few tokens feed UMMA-N,
-//     so streaming the weights at HBM speed is the only cost; split-K spreads short N over all
-//     SMs, partials are summed in a fixed order by the last-arriving CTA (deterministic).
+//     so streaming the weights at HBM speed is the only cost.  Work is scheduled STREAM-K style:
+//     the (tile x k-block) unit space is cut into one equal contiguous range per CTA, so every SM
+//     streams the same number of weight bytes whatever N is (32 tiles or 1002); a tile that is
+//     shared by several CTAs is summed from fp32 partials by its last-arriving CTA in a fixed
+//     order (bit-deterministic, no atomics on data).
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
 // warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global).
@@ -37,9 +40,10 @@ struct GemmParams {
   int64_t x_rows;    // rows of the 128-lane operand (M normal, N swapped)
   int64_t y_rows;    // rows of the BN operand
   int64_t y_rows_w;  // SILU_MUL: offset (rows) of the "up" half inside W
-  int x_tiles, y_tiles, splits, kblocks;
+  int x_tiles, y_tiles, kblocks;
+  int streamk;       // 0: whole tiles, strided over CTAs; 1: equal unit ranges (decode regime)
   int out_f32;
-  float* ws;        // split-K partials  [item][col][lane]
+  float* ws;        // stream-K partials: [cta][2][lane][col]
   int* counters;    // one per tile
 };
 
@@ -54,6 +58,50 @@ template <int BN>
 __host__ __device__ constexpr int gemm_smem_bytes() {
   return gemm_stages<BN>() * gemm_stage_bytes<BN>() + 1024 /*align*/ + 256 /*barriers*/;
 }
+
+// A CTA's work list: segments (tile, [kb0, kb1)).  All three warp roles walk it identically.
+struct SegIter {
+  int kblocks, num_tiles, streamk;
+  long long u, u_end;  // stream-K: current unit, end of this CTA's range
+  int w;               // whole-tile mode: next tile
+  int nseg;            // segments handed out so far
+  __device__ __forceinline__ static long long range_start(long long c, long long units, long long g) {
+    return c * units / g;
+  }
+  __device__ __forceinline__ void init(const GemmParams& p) {
+    kblocks = p.kblocks;
+    num_tiles = p.x_tiles * p.y_tiles;
+    streamk = p.streamk;
+    nseg = 0;
+    if (streamk) {
+      const long long units = static_cast<long long>(num_tiles) * kblocks;
+      u = range_start(blockIdx.x, units, gridDim.x);
+      u_end = range_start(blockIdx.x + 1, units, gridDim.x);
+    } else {
+      w = blockIdx.x;
+    }
+  }
+  // slot: which of the CTA's two partial buffers a partial segment uses (0 = first segment)
+  __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1, int& slot) {
+    if (streamk) {
+      if (u >= u_end) return false;
+      tile = static_cast<int>(u / kblocks);
+      kb0 = static_cast<int>(u - static_cast<long long>(tile) * kblocks);
+      const long long left = u_end - u;
+      kb1 = (kblocks - kb0) < left ? kblocks : kb0 + static_cast<int>(left);
+      u += kb1 - kb0;
+    } else {
+      if (w >= num_tiles) return false;
+      tile = w;
+      kb0 = 0;
+      kb1 = kblocks;
+      w += gridDim.x;
+    }
+    slot = nseg == 0 ? 0 : 1;
+    ++nseg;
+    return true;
+  }
+};
 
 // kSwap: D[i][j] -> C[j][n0+i]   else D[i][j] -> C[m0+i][n0+j]
 // kEpi == SPD_EPI_SILU_MUL (normal mode only): Y tile = [BN/2 gate rows | BN/2 up rows]
@@ -112,21 +160,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   // everything above overlaps the previous kernel's tail under PDL
   griddep_wait();
 
-  const int num_tiles = p.x_tiles * p.y_tiles;
-  const int total = num_tiles * p.splits;
-  const int kb_per = (p.kblocks + p.splits - 1) / p.splits;
-
   if (warp == 0) {
     if (elect_one()) {
       // operand cache policy: in the decode regime the weights (X) stream through once
       const uint64_t polX = kSwap ? kEvictFirst : kEvictNormal;
       const uint64_t polY = kSwap ? kEvictLast : kEvictNormal;
       int stage = 0, phase = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int tile = w / p.splits, split = w - tile * p.splits;
+      SegIter it;
+      it.init(p);
+      int tile, kb0, kb1, slot;
+      while (it.next(tile, kb0, kb1, slot)) {
         const int xt = tile % p.x_tiles, yt = tile / p.x_tiles;
-        const int kb0 = split * kb_per;
-        const int kb1 = min(kb0 + kb_per, p.kblocks);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], kXBytes + kYBytes);
@@ -145,12 +189,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc<T>(kBM, BN, 0, 0);
-      int stage = 0, phase = 0, it = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        const int tile = w / p.splits, split = w - tile * p.splits;
-        const int kb0 = split * kb_per;
-        const int kb1 = min(kb0 + kb_per, p.kblocks);
-        const int as = it & 1, aphase = (it >> 1) & 1;
+      int stage = 0, phase = 0, n = 0;
+      SegIter it;
+      it.init(p);
+      int tile, kb0, kb1, slot;
+      while (it.next(tile, kb0, kb1, slot)) {
+        const int as = n & 1, aphase = (n >> 1) & 1;
+        ++n;
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -175,19 +220,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;     // D row == TMEM lane
     const int et = threadIdx.x - 128;  // 0..127 among the epilogue threads
-    int it = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-      const int tile = w / p.splits, split = w - tile * p.splits;
+    const long long units = static_cast<long long>(p.x_tiles) * p.y_tiles * p.kblocks;
+    int n = 0;
+    SegIter it;
+    it.init(p);
+    int tile, kb0, kb1, slot;
+    while (it.next(tile, kb0, kb1, slot)) {
       const int xt = tile % p.x_tiles, yt = tile / p.x_tiles;
-      const int as = it & 1, aphase = (it >> 1) & 1;
+      const int as = n & 1, aphase = (n >> 1) & 1;
+      ++n;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      const bool complete = (kb0 == 0 && kb1 == p.kblocks);
       bool do_store = true;
+      int c_first = 0, c_last = 0;
 
-      if (p.splits > 1) {
-        // dump the fp32 partial, then the last-arriving split of this tile reduces all of them
-        float* mine = p.ws + (static_cast<size_t>(tile) * p.splits + split) * (kBM * BN);
+      if (!complete) {
+        // dump this CTA's fp32 partial ([lane][col], each thread owns one contiguous row), then
+        // the last-arriving contributor of the tile sums all of them
+        float* mine = p.ws + (static_cast<size_t>(blockIdx.x) * 2 + slot) * (kBM * BN) + row * BN;
 #pragma unroll 1
         for (int c = 0; c < BN; c += kChunk) {
           uint32_t r[kChunk];
@@ -195,31 +247,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
           else tmem_ld_32x32b_x16(taddr + c, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < kChunk; ++j) mine[(c + j) * kBM + row] = __uint_as_float(r[j]);
+          for (int j = 0; j < kChunk; j += 4)
+            *reinterpret_cast<uint4*>(mine + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
         }
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[as]);
+        // contributors of this tile = the CTAs whose unit ranges intersect it
+        const long long t0 = static_cast<long long>(tile) * p.kblocks;
+        c_first = static_cast<int>(((t0 + 1) * gridDim.x - 1) / units);
+        c_last = static_cast<int>(((t0 + p.kblocks) * gridDim.x - 1) / units);
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) *flag_slot = atomicAdd(&p.counters[tile], 1);
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        do_store = (*flag_slot == p.splits - 1);
+        do_store = (*flag_slot == c_last - c_first);
         if (do_store) __threadfence();
       }
 
       if (do_store) {
-        const float* part = p.ws + static_cast<size_t>(tile) * p.splits * (kBM * BN);
 #pragma unroll 1
         for (int c = 0; c < kBNOut; c += kChunk) {
           float v[kChunk];
-          if (p.splits > 1) {
+          if (!complete) {
 #pragma unroll
             for (int j = 0; j < kChunk; ++j) v[j] = 0.f;
-            for (int s = 0; s < p.splits; ++s) {
-              const float* ps = part + static_cast<size_t>(s) * (kBM * BN);
+            // fixed summation order (ascending CTA = ascending k) -> deterministic
+            for (int cc = c_first; cc <= c_last; ++cc) {
+              // a contributor's piece of this tile is its FIRST segment iff its range starts in it
+              const long long st = SegIter::range_start(cc, units, gridDim.x);
+              const int sl = (st / p.kblocks == tile) ? 0 : 1;
+              const float* ps = p.ws + (static_cast<size_t>(cc) * 2 + sl) * (kBM * BN) + row * BN + c;
 #pragma unroll
-              for (int j = 0; j < kChunk; ++j) v[j] += __ldcg(&ps[(c + j) * kBM + row]);
+              for (int j = 0; j < kChunk; j += 4) {
+                const float4 f = __ldcg(reinterpret_cast<const float4*>(ps + j));
+                v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
+              }
             }
           } else {
             uint32_t r[kChunk];
@@ -276,26 +339,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             }
           } else {
             // swapped: lane index runs along N (contiguous in C), column j is the token
-            const int64_t n = static_cast<int64_t>(xt) * kBM + row;
-            if (n < p.x_rows) {
+            const int64_t nn = static_cast<int64_t>(xt) * kBM + row;
+            if (nn < p.x_rows) {
 #pragma unroll
               for (int j = 0; j < kChunk; ++j) {
                 const int64_t m = static_cast<int64_t>(yt) * BN + c + j;
                 if (m < p.y_rows) {
                   if (p.out_f32)
-                    reinterpret_cast<float*>(p.C)[m * p.ldc + n] = to_f32<T>(from_f32<T>(v[j]));
+                    reinterpret_cast<float*>(p.C)[m * p.ldc + nn] = to_f32<T>(from_f32<T>(v[j]));
                   else
-                    reinterpret_cast<T*>(p.C)[m * p.ldc + n] = from_f32<T>(v[j]);
+                    reinterpret_cast<T*>(p.C)[m * p.ldc + nn] = from_f32<T>(v[j]);
                 }
               }
             }
           }
         }
-        if (p.splits > 1) {
-          if (et == 0) p.counters[tile] = 0;  // re-arm for the next launch / graph replay
-        }
+        if (!complete && et == 0) p.counters[tile] = 0;  // re-arm for the next launch / graph replay
       }
-      if (p.splits == 1) {
+      if (complete) {
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[as]);
@@ -359,7 +420,7 @@ int get_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, u
   return 0;
 }
 
-constexpr int64_t kGemmWsBytes = 48ll << 20;  // split-K partials
+constexpr int64_t kGemmWsBytes = 48ll << 20;  // stream-K partials: 2 per CTA
 constexpr int kGemmCounters = 4096;
 
 template <typename T, int BN, bool kSwap, int kEpi>
@@ -409,7 +470,7 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
   p.ldc = ldc;
   p.kblocks = kblocks;
   p.out_f32 = out_f32;
-  p.splits = 1;
+  p.streamk = 0;
   p.ws = reinterpret_cast<float*>(workspace);
   p.counters = workspace ? reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + kGemmWsBytes)
                          : nullptr;
@@ -424,25 +485,18 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
     p.y_rows = M;
     p.x_tiles = static_cast<int>((N + kBM - 1) / kBM);
     p.y_tiles = 1;
-    // split-K so that every SM streams weights; keep >= 4 k-blocks per split
-    int splits = 1;
+    const long long units = static_cast<long long>(p.x_tiles) * kblocks;
+    int grid = static_cast<int>(p.x_tiles < sms ? p.x_tiles : sms);
     if (workspace && workspace_bytes >= spd_gemm_workspace_bytes() && p.x_tiles <= kGemmCounters) {
-      // cost model: rounds of equal work items per CTA, plus a small charge per extra split for
-      // the fp32 partial round trip (mostly L2)
-      const int max_by_k = kblocks / 4 > 0 ? kblocks / 4 : 1;
-      double best = 1e30;
-      for (int s = 1; s <= 16 && s <= max_by_k; ++s) {
-        if (static_cast<int64_t>(p.x_tiles) * s * kBM * BN * 4 > kGemmWsBytes) break;
-        // an empty trailing split would leave an accumulator undefined
-        if (s > 1 && (s - 1) * ((kblocks + s - 1) / s) >= kblocks) continue;
-        const int rounds = (p.x_tiles * s + sms - 1) / sms;
-        const double cost = static_cast<double>(rounds) / s + 0.03 * (s - 1);
-        if (cost < best - 1e-9) { best = cost; splits = s; }
-      }
+      // stream-K: one equal unit range per SM, but never so thin that a tile is shared by more
+      // than ~8 CTAs (the fix-up reads one partial per contributor) or a CTA gets < 4 k-blocks
+      long long g = sms;
+      const long long min_units = kblocks / 8 > 4 ? kblocks / 8 : 4;
+      if (units / g < min_units) g = units / min_units > 0 ? units / min_units : 1;
+      if (g * 2 * kBM * BN * 4 > kGemmWsBytes) g = kGemmWsBytes / (2ll * kBM * BN * 4);
+      grid = static_cast<int>(g);
+      p.streamk = 1;
     }
-    p.splits = splits;
-    const int total = p.x_tiles * splits;
-    const int grid = total < sms ? total : sms;
     if ((rc = get_tmap(&tx, W, N, K, ldw, kBM))) return rc;
     if ((rc = get_tmap(&ty, A, M, K, lda, BN))) return rc;
 #define SPD_GEMM_SWAP(BN_)                                                               \
