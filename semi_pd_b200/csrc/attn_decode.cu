@@ -368,7 +368,11 @@ attn_decode_kernel(const DecodeParams p) {
             m_ref[g] = m_new;
           }
           if (j > 0) {
-            mbar_wait(o_done, (t - 1) & 1);  // O^T stable: PV_{t-1} complete
+            // O^T stable once PV_{t-1} is complete.  That completion is observed on p_empty (committed
+            // with every PV): this thread waited for the PREVIOUS phase of that barrier at tile t-1,
+            // so the parity wait cannot alias — a per-PV barrier that is only waited on now and then
+            // (the softmax may run up to two PVs ahead) would.
+            mbar_wait(&p_empty[(t - 1) & 1], ((t - 1) >> 1) & 1);
             tc_fence_after_sync();
             uint32_t o[16];
             tmem_ld_32x32b_x16(tmem_O + lane_base + ob * kDcN, o);
@@ -408,7 +412,7 @@ attn_decode_kernel(const DecodeParams p) {
       for (int g = 0; g < kDcMaxGroup; ++g)
         l_tot[g] = (red[g] + red[8 + g]) + (red[16 + g] + red[24 + g]);
       if (it.n_tiles > 0) {
-        mbar_wait(o_done, (t - 1) & 1);
+        mbar_wait(&p_empty[(t - 1) & 1], ((t - 1) >> 1) & 1);  // last PV of the item complete
         tc_fence_after_sync();
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_O + lane_base + ob * kDcN, r);
