@@ -477,24 +477,33 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
   CUtensorMap tx, ty;
   int rc;
 
-  const bool swap = (M <= 256) && epilogue == SPD_EPI_NONE;
+  // stream-K grid: one equal unit range per SM, but never so thin that a tile is shared by more
+  // than ~8 CTAs (the fix-up reads one partial per contributor) or a CTA gets < 4 k-blocks
+  const bool can_streamk = workspace && workspace_bytes >= spd_gemm_workspace_bytes();
+  auto streamk_grid = [&](long long tiles, int BN) -> int {
+    const long long units = tiles * kblocks;
+    long long g = sms;
+    const long long min_units = kblocks / 8 > 4 ? kblocks / 8 : 4;
+    if (units / g < min_units) g = units / min_units > 0 ? units / min_units : 1;
+    if (g * 2 * kBM * BN * 4 > kGemmWsBytes) g = kGemmWsBytes / (2ll * kBM * BN * 4);
+    return static_cast<int>(g);
+  };
+
+  // M <= 64: swap-AB (the token dimension feeds UMMA-N, padded to 16..64).  Beyond that the
+  // re-read of the activation tile by every weight tile would exceed the weight bytes, so
+  // 64 < M <= 256 runs un-swapped 128 x 256 tiles (activation traffic = half the weight traffic),
+  // stream-K scheduled as well.
+  const bool swap = (M <= 64) && epilogue == SPD_EPI_NONE;
   if (swap) {
     int BN = 16;
-    while (BN < M) BN <<= 1;  // 16,32,64,128,256
+    while (BN < M) BN <<= 1;  // 16,32,64
     p.x_rows = N;
     p.y_rows = M;
     p.x_tiles = static_cast<int>((N + kBM - 1) / kBM);
     p.y_tiles = 1;
-    const long long units = static_cast<long long>(p.x_tiles) * kblocks;
     int grid = static_cast<int>(p.x_tiles < sms ? p.x_tiles : sms);
-    if (workspace && workspace_bytes >= spd_gemm_workspace_bytes() && p.x_tiles <= kGemmCounters) {
-      // stream-K: one equal unit range per SM, but never so thin that a tile is shared by more
-      // than ~8 CTAs (the fix-up reads one partial per contributor) or a CTA gets < 4 k-blocks
-      long long g = sms;
-      const long long min_units = kblocks / 8 > 4 ? kblocks / 8 : 4;
-      if (units / g < min_units) g = units / min_units > 0 ? units / min_units : 1;
-      if (g * 2 * kBM * BN * 4 > kGemmWsBytes) g = kGemmWsBytes / (2ll * kBM * BN * 4);
-      grid = static_cast<int>(g);
+    if (can_streamk && p.x_tiles <= kGemmCounters) {
+      grid = streamk_grid(p.x_tiles, BN);
       p.streamk = 1;
     }
     if ((rc = get_tmap(&tx, W, N, K, ldw, kBM))) return rc;
@@ -507,8 +516,6 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
       SPD_GEMM_SWAP(16)
       SPD_GEMM_SWAP(32)
       SPD_GEMM_SWAP(64)
-      SPD_GEMM_SWAP(128)
-      SPD_GEMM_SWAP(256)
     }
 #undef SPD_GEMM_SWAP
     return set_error(SPD_E_SHAPE, "spd_gemm: unreachable BN=%d", BN);
@@ -534,7 +541,11 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
     const int BN = use256 ? 256 : 128;
     p.y_tiles = static_cast<int>((N + BN - 1) / BN);
     const int total = p.x_tiles * p.y_tiles;
-    const int grid = total < sms ? total : sms;
+    int grid = total < sms ? total : sms;
+    if (M <= 256 && use256 && can_streamk && total <= kGemmCounters) {
+      grid = streamk_grid(total, BN);  // decode regime, un-swapped
+      p.streamk = 1;
+    }
     if ((rc = get_tmap(&tx, A, M, K, lda, kBM))) return rc;
     if ((rc = get_tmap(&ty, W, N, K, ldw, BN))) return rc;
     if (use256) {
