@@ -19,6 +19,7 @@
 // Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), TMEM double buffer full/empty
 // (MMA <-> epilogue).
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 
@@ -479,11 +480,17 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
 
   // stream-K grid: one equal unit range per SM, but never so thin that a tile is shared by more
   // than ~8 CTAs (the fix-up reads one partial per contributor) or a CTA gets < 4 k-blocks
-  const bool can_streamk = workspace && workspace_bytes >= spd_gemm_workspace_bytes();
+  // tuning knobs (experiments only): SPD_GEMM_STREAMK=0 disables stream-K, SPD_GEMM_SPLIT=d caps
+  // the contributors per tile at ~d, SPD_GEMM_SWAPMAX=m is the largest M routed to swap-AB
+  static const int env_streamk = getenv("SPD_GEMM_STREAMK") ? atoi(getenv("SPD_GEMM_STREAMK")) : 1;
+  static const int env_split = getenv("SPD_GEMM_SPLIT") ? atoi(getenv("SPD_GEMM_SPLIT")) : 8;
+  static const int env_swapmax = getenv("SPD_GEMM_SWAPMAX") ? atoi(getenv("SPD_GEMM_SWAPMAX")) : 64;
+  const bool can_streamk = env_streamk && workspace && workspace_bytes >= spd_gemm_workspace_bytes();
   auto streamk_grid = [&](long long tiles, int BN) -> int {
     const long long units = tiles * kblocks;
     long long g = sms;
-    const long long min_units = kblocks / 8 > 4 ? kblocks / 8 : 4;
+    if (tiles >= sms) return static_cast<int>(g);
+    const long long min_units = kblocks / env_split > 4 ? kblocks / env_split : 4;
     if (units / g < min_units) g = units / min_units > 0 ? units / min_units : 1;
     if (g * 2 * kBM * BN * 4 > kGemmWsBytes) g = kGemmWsBytes / (2ll * kBM * BN * 4);
     return static_cast<int>(g);
@@ -493,10 +500,10 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
   // re-read of the activation tile by every weight tile would exceed the weight bytes, so
   // 64 < M <= 256 runs un-swapped 128 x 256 tiles (activation traffic = half the weight traffic),
   // stream-K scheduled as well.
-  const bool swap = (M <= 64) && epilogue == SPD_EPI_NONE;
+  const bool swap = (M <= env_swapmax) && epilogue == SPD_EPI_NONE;
   if (swap) {
     int BN = 16;
-    while (BN < M) BN <<= 1;  // 16,32,64
+    while (BN < M) BN <<= 1;  // 16,32,64 (128, 256 only when SPD_GEMM_SWAPMAX raises the limit)
     p.x_rows = N;
     p.y_rows = M;
     p.x_tiles = static_cast<int>((N + kBM - 1) / kBM);
@@ -516,6 +523,8 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
       SPD_GEMM_SWAP(16)
       SPD_GEMM_SWAP(32)
       SPD_GEMM_SWAP(64)
+      SPD_GEMM_SWAP(128)
+      SPD_GEMM_SWAP(256)
     }
 #undef SPD_GEMM_SWAP
     return set_error(SPD_E_SHAPE, "spd_gemm: unreachable BN=%d", BN);
