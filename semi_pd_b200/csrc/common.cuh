@@ -60,7 +60,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline cudaStream_t as_stream(spd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int device_sm_count_cached();
-// SPD_PDL=1 in the environment turns on programmatic dependent launch for the per-layer kernels
+// programmatic dependent launch for the per-layer kernels (SPD_PDL=0 in the environment disables it)
 bool pdl_enabled();
 
 // launch helper: optional programmatic-dependent-launch attribute.  Every kernel launched through

@@ -482,24 +482,26 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
   // than ~8 CTAs (the fix-up reads one partial per contributor) or a CTA gets < 4 k-blocks
   // tuning knobs (experiments only): SPD_GEMM_STREAMK=0 disables stream-K, SPD_GEMM_SPLIT=d caps
   // the contributors per tile at ~d, SPD_GEMM_SWAPMAX=m is the largest M routed to swap-AB
+  // Measured on B200 (scripts/bench_gemm_decode.py, profiles/r01_gemm_decode_sweep.log): one SM
+  // streams ~90-100 GB/s, the global-memory fix-up of a shared tile costs ~8 us, so K is only
+  // split when few tiles would each stream a long K (down_proj: 32 tiles x 224 k-blocks).
   static const int env_streamk = getenv("SPD_GEMM_STREAMK") ? atoi(getenv("SPD_GEMM_STREAMK")) : 1;
-  static const int env_split = getenv("SPD_GEMM_SPLIT") ? atoi(getenv("SPD_GEMM_SPLIT")) : 8;
-  static const int env_swapmax = getenv("SPD_GEMM_SWAPMAX") ? atoi(getenv("SPD_GEMM_SWAPMAX")) : 64;
-  const bool can_streamk = env_streamk && workspace && workspace_bytes >= spd_gemm_workspace_bytes();
+  static const int env_split = getenv("SPD_GEMM_SPLIT") ? atoi(getenv("SPD_GEMM_SPLIT")) : 4;
+  static const int env_swapmax = getenv("SPD_GEMM_SWAPMAX") ? atoi(getenv("SPD_GEMM_SWAPMAX")) : 128;
+  const bool ws_ok = env_streamk && workspace && workspace_bytes >= spd_gemm_workspace_bytes();
+  const bool can_streamk = ws_ok && (env_streamk == 2 || kblocks >= 128);
   auto streamk_grid = [&](long long tiles, int BN) -> int {
     const long long units = tiles * kblocks;
     long long g = sms;
-    if (tiles >= sms) return static_cast<int>(g);
     const long long min_units = kblocks / env_split > 4 ? kblocks / env_split : 4;
     if (units / g < min_units) g = units / min_units > 0 ? units / min_units : 1;
     if (g * 2 * kBM * BN * 4 > kGemmWsBytes) g = kGemmWsBytes / (2ll * kBM * BN * 4);
     return static_cast<int>(g);
   };
 
-  // M <= 64: swap-AB (the token dimension feeds UMMA-N, padded to 16..64).  Beyond that the
-  // re-read of the activation tile by every weight tile would exceed the weight bytes, so
-  // 64 < M <= 256 runs un-swapped 128 x 256 tiles (activation traffic = half the weight traffic),
-  // stream-K scheduled as well.
+  // M <= 128: swap-AB (the token dimension feeds UMMA-N, padded to 16..128).  Beyond that the
+  // re-read of the activation tile by every weight tile dominates, so 128 < M <= 256 runs
+  // un-swapped 128 x 256 tiles (activation traffic = half the weight traffic).
   const bool swap = (M <= env_swapmax) && epilogue == SPD_EPI_NONE;
   if (swap) {
     int BN = 16;
@@ -509,7 +511,7 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
     p.x_tiles = static_cast<int>((N + kBM - 1) / kBM);
     p.y_tiles = 1;
     int grid = static_cast<int>(p.x_tiles < sms ? p.x_tiles : sms);
-    if (can_streamk && p.x_tiles <= kGemmCounters) {
+    if (can_streamk && p.x_tiles <= kGemmCounters && (env_streamk == 2 || p.x_tiles * 2 <= sms)) {
       grid = streamk_grid(p.x_tiles, BN);
       p.streamk = 1;
     }
@@ -551,7 +553,8 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
     p.y_tiles = static_cast<int>((N + BN - 1) / BN);
     const int total = p.x_tiles * p.y_tiles;
     int grid = total < sms ? total : sms;
-    if (M <= 256 && use256 && can_streamk && total <= kGemmCounters) {
+    if (M <= 256 && use256 && can_streamk && total <= kGemmCounters &&
+        (env_streamk == 2 || total * 2 <= sms)) {
       grid = streamk_grid(total, BN);  // decode regime, un-swapped
       p.streamk = 1;
     }

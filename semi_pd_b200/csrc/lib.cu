@@ -33,8 +33,8 @@ int device_sm_count_cached() {
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("SPD_PDL");
-    v = (e && e[0] == '1') ? 1 : 0;
+    const char* e = getenv("SPD_PDL");  // on by default; SPD_PDL=0 turns it off
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }
