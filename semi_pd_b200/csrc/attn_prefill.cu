@@ -5,17 +5,20 @@
 // Semantics: S/layers/attention/torch_native_backend.py:26-109.
 //
 // CTA = 128 query rows of one request x one query head (grid: q-tile (heaviest first), head,
-// request; CTAs past a request's length exit).  KV is visited in 128-token tiles:
-//   loaders  (warps 4-7): gather K/V rows through req_to_token with 16-byte cp.async into
-//                         128-byte-swizzled smem (page size is 1 token, so rows are scattered);
-//   MMA      (warp 8)   : S_j = Q K_j^T (K-major operands), O += P_j V_j (V as MN-major operand);
-//                         S is double-buffered in TMEM so S_{j+1} is computed while the softmax
-//                         of tile j runs;
-//   softmax  (warps 0-3): one thread per query row — TMEM -> registers, mask, online softmax in
-//                         the exp2 domain with LAZY rescaling (O in TMEM is only rescaled when a
-//                         row max grows by > 2^8), P -> smem as the A operand of the PV MMA,
-//                         final O / l -> global.
-// Q arrives by TMA.  TMEM: S0 | S1 | O = 384 of 512 columns.
+// request; CTAs past a request's length exit).  KV is visited in 128-token tiles; EVEN tiles
+// belong to softmax warpgroup 0, ODD tiles to warpgroup 1.  Each warpgroup runs an independent
+// online softmax (own running max m, row sum l, own S buffer, own P buffer, own O accumulator
+// in TMEM), so two tiles are in softmax at any time while the tensor core works on the next
+// S / previous PV; the two (m, l, O) triples are merged in the epilogue like a 2-way split-KV.
+//   K loaders (warps 8-9), V loaders (warps 10-11): gather rows through req_to_token with
+//       16-byte cp.async into 128-byte-swizzled smem; K and V rings are released separately
+//       (K_j right after S_j, V_j after PV_j), so K runs well ahead of V;
+//   MMA (warp 12): S_j = Q K_j^T (K-major operands), O_g += P_j V_j (V as MN-major operand),
+//       issue order S0 S1 | PV0 S2 | PV1 S3 | ...;
+//   softmax (warps 0-3 / 4-7): one thread per query row; ONE pass per tile in the exp2 domain
+//       against a lazily raised reference max (O in TMEM is rescaled only when a row max grows by
+//       more than 2^8 — then the tile is redone, which besides the first tile is rare).
+// Q arrives by TMA.  TMEM: S0 | S1 | O0 | O1 = 512 columns.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -24,12 +27,12 @@
 
 namespace spd {
 
-constexpr int kPfThreads = 288;
+constexpr int kPfThreads = 416;  // 8 softmax + 2 K-loader + 2 V-loader + 1 MMA warps
 constexpr int kPfM = 128;    // query rows per CTA
 constexpr int kPfN = 128;    // kv tokens per tile
 constexpr int kPfD = 128;    // head dim
 constexpr int kTileBytes = 128 * 128 * 2;  // one [128 x 128] 16-bit tile = two 16 KB swizzle blocks
-constexpr int kPfSmem = kTileBytes * 6 + 1024 + 256;  // Q, K0, K1, V0, V1, P + align + barriers
+constexpr int kPfSmem = kTileBytes * 7 + 1024 + 512;  // Q, K0, K1, V0, V1, P0, P1 + align + barriers
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 struct PrefillParams {
@@ -53,6 +56,43 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk16) {
   return (chunk16 >> 3) * 16384 + row * 128 + (((chunk16 & 7) ^ (row & 7)) << 4);
 }
 
+// One tile row for one thread: S (TMEM) -> p = exp2(s*scale - m_off) -> P (smem, 16-bit).
+// Returns the row sum of p and (in mx) the max raw score seen, mask applied.
+template <typename T>
+__device__ __forceinline__ float softmax_row_pass(uint32_t ts, uint8_t* sP, int row, float scale_log2,
+                                                  float m_off, bool need_mask, int kv0, int limit,
+                                                  float& mx) {
+  float psum = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < kPfN; c += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(ts + c, r);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float s0 = __uint_as_float(r[i]), s1 = __uint_as_float(r[i + 1]);
+      float p0 = fast_exp2(s0 * scale_log2 - m_off);
+      float p1 = fast_exp2(s1 * scale_log2 - m_off);
+      if (need_mask) {
+        const bool v0 = (kv0 + c + i) <= limit, v1 = (kv0 + c + i + 1) <= limit;
+        p0 = v0 ? p0 : 0.f;
+        p1 = v1 ? p1 : 0.f;
+        mx = fmaxf(mx, fmaxf(v0 ? s0 : -INFINITY, v1 ? s1 : -INFINITY));
+      } else {
+        mx = fmaxf(mx, fmaxf(s0, s1));
+      }
+      psum += p0 + p1;
+      pk[i >> 1] = pack2<T>(p0, p1);
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      *reinterpret_cast<uint4*>(sP + tile_off(row, (c >> 3) + ch)) =
+          make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+  }
+  return psum;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kPfThreads, 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams p) {
@@ -74,32 +114,36 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kTileBytes;      // 2 stages
   uint8_t* sV = smem + 3 * kTileBytes;  // 2 stages
-  uint8_t* sP = smem + 5 * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * kTileBytes);
+  uint8_t* sP = smem + 5 * kTileBytes;  // one per warpgroup
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTileBytes);
   uint64_t* q_full = bars;          // 1
-  uint64_t* kv_full = bars + 1;     // 2
-  uint64_t* kv_empty = bars + 3;    // 2
-  uint64_t* s_full = bars + 5;      // 2
-  uint64_t* s_empty = bars + 7;     // 2
-  uint64_t* p_full = bars + 9;      // 1
-  uint64_t* o_done = bars + 10;     // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* k_full = bars + 1;      // 2
+  uint64_t* k_empty = bars + 3;     // 2
+  uint64_t* v_full = bars + 5;      // 2
+  uint64_t* v_empty = bars + 7;     // 2
+  uint64_t* s_full = bars + 9;      // 2 (per warpgroup)
+  uint64_t* s_empty = bars + 11;    // 2
+  uint64_t* p_full = bars + 13;     // 2
+  uint64_t* pv_done = bars + 15;    // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 8) {
+  if (warp == 12) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       mbar_init(q_full, 1);
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&kv_full[i], 128);
-        mbar_init(&kv_empty[i], 1);
+        mbar_init(&k_full[i], 64);
+        mbar_init(&k_empty[i], 1);
+        mbar_init(&v_full[i], 64);
+        mbar_init(&v_empty[i], 1);
         mbar_init(&s_full[i], 1);
         mbar_init(&s_empty[i], 4);
+        mbar_init(&p_full[i], 4);
+        mbar_init(&pv_done[i], 1);
       }
-      mbar_init(p_full, 4);
-      mbar_init(o_done, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -110,12 +154,12 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
-  const uint32_t tmem_O = tmem_base + 256;  // 128 columns
+  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns (warpgroup 0 / 1)
+  const uint32_t tmem_O = tmem_base + 256;  // 2 x 128 columns
 
   griddep_wait();
 
-  if (warp == 8) {
+  if (warp == 12) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       mbar_expect_tx(q_full, kTileBytes);
@@ -123,162 +167,139 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
       tma_load_2d(sQ + 16384, &tmQ, q_full, head * kPfD + 64, q_row0, kEvictFirst);
       constexpr uint32_t idesc_qk = umma_idesc<T>(kPfM, kPfN, 0, 0);  // A, B K-major
       constexpr uint32_t idesc_pv = umma_idesc<T>(kPfM, kPfD, 0, 1);  // B (V) MN-major
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      const uint32_t q_addr = smem_u32(sQ);
       auto issue_qk = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
-        mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
+        const int g = j & 1, u = j >> 1;
+        mbar_wait(&k_full[g], u & 1);
+        mbar_wait(&s_empty[g], (u & 1) ^ 1);
         tc_fence_after_sync();
-        const uint32_t k_addr = smem_u32(sK + st * kTileBytes);
+        const uint32_t k_addr = smem_u32(sK + g * kTileBytes);
 #pragma unroll
         for (int k = 0; k < kPfD / 16; ++k) {
           const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_ss(tmem_S + st * kPfN, umma_desc_sw128(q_addr + off, 16, 1024),
+          umma_ss(tmem_S + g * kPfN, umma_desc_sw128(q_addr + off, 16, 1024),
                   umma_desc_sw128(k_addr + off, 16, 1024), idesc_qk, k > 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[st]);
+        umma_commit(&s_full[g]);
+        umma_commit(&k_empty[g]);  // K stage free as soon as S_j is done
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
+      if (n_tiles > 1) issue_qk(1);
       for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) issue_qk(j + 1);
-        mbar_wait(p_full, j & 1);
+        const int g = j & 1, u = j >> 1;
+        mbar_wait(&p_full[g], u & 1);
+        mbar_wait(&v_full[g], u & 1);
         tc_fence_after_sync();
-        const uint32_t v_addr = smem_u32(sV + (j & 1) * kTileBytes);
+        const uint32_t v_addr = smem_u32(sV + g * kTileBytes);
+        const uint32_t p_addr = smem_u32(sP + g * kTileBytes);
 #pragma unroll
         for (int k = 0; k < kPfN / 16; ++k) {
           // A = P[128 x 16 kv] (K-major), B = V[16 kv x 128 d] (MN-major: 2 blocks of 64 d,
           // LBO = 16 KB; kv rows 128 B apart, 8-row groups SBO = 1 KB)
           const uint32_t a_off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_ss(tmem_O, umma_desc_sw128(p_addr + a_off, 16, 1024),
+          umma_ss(tmem_O + g * kPfD, umma_desc_sw128(p_addr + a_off, 16, 1024),
                   umma_desc_sw128(v_addr + k * 2048, 16384, 1024), idesc_pv,
-                  (j > 0 || k > 0) ? 1u : 0u);
+                  (u > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&kv_empty[j & 1]);
-        umma_commit(o_done);
+        umma_commit(&v_empty[g]);
+        umma_commit(&pv_done[g]);
+        if (j + 2 < n_tiles) issue_qk(j + 2);
       }
     }
-  } else if (warp >= 4) {
-    // ===================== K/V gather loaders (128 threads) =====================
-    const int lt = threadIdx.x - 128;
+  } else if (warp >= 8) {
+    // ===================== K loaders (warps 8-9) / V loaders (warps 10-11) =====================
+    const bool is_v = warp >= 10;
+    const int lt = (threadIdx.x - 256) & 63;
     const int chunk = lt & 15;   // 16-byte chunk of the 256-byte head row
-    const int rsub = lt >> 4;    // 0..7
-    const T* kp = reinterpret_cast<const T*>(p.k_pool);
-    const T* vp = reinterpret_cast<const T*>(p.v_pool);
+    const int rsub = lt >> 4;    // 0..3
+    const T* pool = reinterpret_cast<const T*>(is_v ? p.v_pool : p.k_pool);
+    uint8_t* sbase = is_v ? sV : sK;
+    uint64_t* full = is_v ? v_full : k_full;
+    uint64_t* empty = is_v ? v_empty : k_empty;
     const int32_t* rtt = p.req_to_token + p.req_pool_indices[req] * p.rtt_stride;
     const int64_t row_elems = static_cast<int64_t>(p.Hk) * kPfD;
     const int64_t col = static_cast<int64_t>(hk) * kPfD + chunk * 8;
-    // Double buffering: tile j is gathered while tile j-1 is being consumed.  Tile j-1 is
-    // published BEFORE waiting for tile j's stage, otherwise the MMA warp (which needs K_{j-1}
-    // before it can retire PV_{j-2} and free that stage) and the loaders would wait on each other.
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j & 1;
       // page-table lookups first, all in flight together and overlapped with the waits below (the
-      // cp.async asm is a compiler barrier; interleaving the lookups with it would serialise 16
-      // dependent global-load latencies per tile)
-      int slot[16];
+      // cp.async asm is a compiler barrier; interleaving the lookups with it would serialise the
+      // dependent global-load latencies)
+      int slot[32];
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int kv = j * kPfN + it * 8 + rsub;
+      for (int it = 0; it < 32; ++it) {
+        const int kv = j * kPfN + it * 4 + rsub;
         slot[it] = kv < kv_len ? __ldg(rtt + kv) : -1;
       }
+      // publish the previous tile BEFORE waiting for this tile's stage (see the MMA issue order:
+      // the consumer of tile j-1 must never wait on the producer waiting on the consumer)
       if (j > 0) {
         cp_async_wait<0>();
         fence_proxy_async_smem();
-        mbar_arrive(&kv_full[(j - 1) & 1]);
+        mbar_arrive(&full[(j - 1) & 1]);
       }
-      mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-      const uint32_t kdst = smem_u32(sK + st * kTileBytes);
-      const uint32_t vdst = smem_u32(sV + st * kTileBytes);
+      mbar_wait(&empty[st], ((j >> 1) & 1) ^ 1);
+      const uint32_t dst = smem_u32(sbase + st * kTileBytes);
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int row = it * 8 + rsub;
+      for (int it = 0; it < 32; ++it) {
+        const int row = it * 4 + rsub;
         const bool valid = slot[it] >= 0;
         const int64_t s64 = valid ? slot[it] : 0;
-        const uint32_t off = tile_off(row, chunk);
-        cp_async16(kdst + off, kp + s64 * row_elems + col, valid);
-        cp_async16(vdst + off, vp + s64 * row_elems + col, valid);
+        cp_async16(dst + tile_off(row, chunk), pool + s64 * row_elems + col, valid);
       }
       cp_async_commit();
     }
     cp_async_wait<0>();
     fence_proxy_async_smem();
-    mbar_arrive(&kv_full[(n_tiles - 1) & 1]);
+    mbar_arrive(&full[(n_tiles - 1) & 1]);
   } else {
-    // ===================== softmax / correction / epilogue (one thread per query row) ==========
-    const int row = threadIdx.x;  // == TMEM lane
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    const int limit = pre + m0 + row;  // last visible key of this row (causal)
-    float m_used = -INFINITY;  // max currently folded into O and l (raw score units)
+    // ===================== softmax warpgroups (one thread per query row) =====================
+    const int g = warp >> 2;            // warpgroup: 0 = even tiles, 1 = odd tiles
+    const int row = threadIdx.x & 127;  // == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int limit = pre + m0 + row;   // last visible key of this row (causal)
+    const uint32_t ts = tmem_S + lane_base + g * kPfN;
+    const uint32_t to = tmem_O + lane_base + g * kPfD;
+    uint8_t* myP = sP + g * kTileBytes;
+    float m_used = -INFINITY;  // max currently folded into O_g and l (raw score units)
     float l = 0.f;
     const float thr = kRescaleThreshold / p.scale_log2;
-    for (int j = 0; j < n_tiles; ++j) {
-      const int b = j & 1;
-      mbar_wait(&s_full[b], (j >> 1) & 1);
+    int u = 0;
+    for (int j = g; j < n_tiles; j += 2, ++u) {
+      const int kv0 = j * kPfN;
+      const bool need_mask = (kv0 + kPfN - 1) > (pre + m0);
+      mbar_wait(&s_full[g], u & 1);
       tc_fence_after_sync();
-      const uint32_t ts = tmem_S + lane_base + b * kPfN;
-      const bool need_mask = (j * kPfN + kPfN - 1) > (pre + m0);
-      // pass 1: row max
-      float mx = -INFINITY;
+      if (u == 0) {
+        // first tile of this warpgroup: establish the reference max with a max-only pre-pass
+        float mx0 = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < kPfN; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(ts + c, r);
-        tmem_ld_wait();
-        if (need_mask) {
+        for (int c = 0; c < kPfN; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(ts + c, r);
+          tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (j * kPfN + c + i <= limit) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+            if (!need_mask || (kv0 + c + i) <= limit) mx0 = fmaxf(mx0, __uint_as_float(r[i]));
         }
+        m_used = mx0;
+      } else {
+        // P_g / O_g are free once this warpgroup's previous PV has completed
+        mbar_wait(&pv_done[g], (u - 1) & 1);
+        tc_fence_after_sync();
       }
-      // lazy rescale decision is warp-uniform (tcgen05.ld/st are warp-collective)
-      const bool grow = mx > m_used + thr;
-      const bool do_rescale = __any_sync(0xffffffffu, grow);
-      float alpha = 1.f;
-      if (do_rescale) {
+      float m_off = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
+      float mx = -INFINITY;
+      float psum = softmax_row_pass<T>(ts, myP, row, p.scale_log2, m_off, need_mask, kv0, limit, mx);
+      // raise the reference max only when some row outgrew it by > 2^8 (warp-uniform decision:
+      // tcgen05.ld/st are warp-collective); then redo the tile against the new max
+      if (__any_sync(0xffffffffu, mx > m_used + thr)) {
         const float m_new = fmaxf(m_used, mx);
-        alpha = (m_used == -INFINITY) ? 0.f : exp2f((m_used - m_new) * p.scale_log2);
+        const float alpha = (m_used == -INFINITY) ? 0.f : fast_exp2((m_used - m_new) * p.scale_log2);
         l *= alpha;
         m_used = m_new;
-      }
-      const float m_off = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
-      // pass 2: p = exp2(s * scale - m), packed to 16-bit in registers
-      uint32_t pk[kPfN / 2];
-      float psum = 0.f;
-#pragma unroll
-      for (int c = 0; c < kPfN; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(ts + c, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = fast_exp2(__uint_as_float(r[i]) * p.scale_log2 - m_off);
-          float p1 = fast_exp2(__uint_as_float(r[i + 1]) * p.scale_log2 - m_off);
-          if (need_mask) {
-            if (j * kPfN + c + i > limit) p0 = 0.f;
-            if (j * kPfN + c + i + 1 > limit) p1 = 0.f;
-          }
-          const uint32_t w = pack2<T>(p0, p1);
-          // accumulate what the tensor core will actually see (the rounded values)
-          const float2 pr = unpack2<T>(w);
-          psum += pr.x + pr.y;
-          pk[(c + i) >> 1] = w;
-        }
-      }
-      l += psum;
-      // S buffer b may now be overwritten by S_{j+2}
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[b]);
-      // P buffer free + O stable once PV_{j-1} has completed
-      if (j > 0) {
-        mbar_wait(o_done, (j - 1) & 1);
-        tc_fence_after_sync();
-        if (do_rescale) {
-          const uint32_t to = tmem_O + lane_base;
+        m_off = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
+        if (u > 0) {
 #pragma unroll 1
           for (int c = 0; c < kPfD; c += 32) {
             uint32_t r[32];
@@ -290,39 +311,68 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
           }
           tmem_st_wait();
         }
+        psum = softmax_row_pass<T>(ts, myP, row, p.scale_log2, m_off, need_mask, kv0, limit, mx);
       }
-      // P -> smem (K-major, 128-byte swizzle): 16 chunks of 8 values
-#pragma unroll
-      for (int ch = 0; ch < 16; ++ch) {
-        uint4 v = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-        *reinterpret_cast<uint4*>(sP + tile_off(row, ch)) = v;
-      }
+      l += psum;
+      // S_g may be overwritten by S_{j+2}; P_g is ready for PV_j
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) {
+        mbar_arrive(&s_empty[g]);
+        mbar_arrive(&p_full[g]);
+      }
     }
-    // epilogue: O / l
-    mbar_wait(o_done, (n_tiles - 1) & 1);
+    // ---- epilogue: merge the two warpgroups' (m, l, O) like a 2-way split-KV ----
+    const int my_tiles = u;  // tiles this warpgroup processed
+    if (my_tiles > 0) {
+      mbar_wait(&pv_done[g], (my_tiles - 1) & 1);
+      tc_fence_after_sync();
+    }
+    // exchange (m, l) through this warpgroup's own (now idle) P buffer
+    float* stats = reinterpret_cast<float*>(myP);
+    stats[row * 2] = m_used;
+    stats[row * 2 + 1] = l;
+    // after this barrier BOTH warpgroups have observed their last PV: O_0 and O_1 are final
+    tc_fence_before_sync();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     tc_fence_after_sync();
-    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    const float* st0 = reinterpret_cast<const float*>(sP);
+    const float* st1 = reinterpret_cast<const float*>(sP + kTileBytes);
+    const float m_e = st0[row * 2], l_e = st0[row * 2 + 1];
+    const float m_o = st1[row * 2], l_o = st1[row * 2 + 1];
+    const bool has_o = n_tiles > 1;
+    const float M = fmaxf(m_e, has_o ? m_o : -INFINITY);
+    const float f_e = (m_e == -INFINITY) ? 0.f : fast_exp2((m_e - M) * p.scale_log2);
+    const float f_o = (!has_o || m_o == -INFINITY) ? 0.f : fast_exp2((m_o - M) * p.scale_log2);
+    const float L = l_e * f_e + (has_o ? l_o * f_o : 0.f);
+    const float inv_l = L > 0.f ? 1.f / L : 0.f;
+    const float w_e = f_e * inv_l, w_o = f_o * inv_l;
     T* dst = reinterpret_cast<T*>(p.out) + static_cast<int64_t>(q_row0 + row) * p.out_stride +
              static_cast<int64_t>(head) * kPfD;
-    const uint32_t to = tmem_O + lane_base;
+    const uint32_t to_e = tmem_O + lane_base, to_o = tmem_O + lane_base + kPfD;
+    // warpgroup 0 writes head-dim columns 0..63, warpgroup 1 columns 64..127
 #pragma unroll 1
-    for (int c = 0; c < kPfD; c += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(to + c, r);
+    for (int c = g * 64; c < g * 64 + 64; c += 32) {
+      uint32_t a[32], b[32];
+      tmem_ld_32x32b_x32(to_e + c, a);
+      if (has_o) tmem_ld_32x32b_x32(to_o + c, b);
       tmem_ld_wait();
       if (row < rows_valid) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-          uint4 o;
-          o.x = pack2<T>(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l);
-          o.y = pack2<T>(__uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
-          o.z = pack2<T>(__uint_as_float(r[i + 4]) * inv_l, __uint_as_float(r[i + 5]) * inv_l);
-          o.w = pack2<T>(__uint_as_float(r[i + 6]) * inv_l, __uint_as_float(r[i + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(dst + c + i) = o;
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            o[k] = __uint_as_float(a[i + k]) * w_e;
+            if (has_o) o[k] += __uint_as_float(b[i + k]) * w_o;
+          }
+          uint4 v;
+          v.x = pack2<T>(o[0], o[1]);
+          v.y = pack2<T>(o[2], o[3]);
+          v.z = pack2<T>(o[4], o[5]);
+          v.w = pack2<T>(o[6], o[7]);
+          *reinterpret_cast<uint4*>(dst + c + i) = v;
         }
       }
     }
@@ -331,7 +381,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
   griddep_launch_dependents();
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == 12) tmem_dealloc(tmem_base, 512);
 }
 
 int check_attn_args(const char* fn, const void* out, const void* q, const void* k_pool,
