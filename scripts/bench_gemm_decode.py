@@ -10,6 +10,7 @@ ops.set_sm_budget(budget)
 
 
 def graph_time(fns, reps=5):
+    torch.cuda.synchronize()  # inputs were produced on the default stream
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         for f in fns:

@@ -16,6 +16,7 @@ torch.manual_seed(0)
 
 def graph_time(fns, reps=5):
     """fns: list of callables launched back to back inside one graph"""
+    torch.cuda.synchronize()  # inputs were produced on the default stream
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         for f in fns:

@@ -57,12 +57,16 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk16) {
 }
 
 // One tile row for one thread: S (TMEM) -> p = exp2(s*scale - m_off) -> P (smem, 16-bit).
-// Returns the row sum of p and (in mx) the max raw score seen, mask applied.
-template <typename T>
+// Returns the row sum of p; pmax receives max(p) (masked entries excluded) — p > 2^8 means the
+// row outgrew the reference max.  kMask is a template parameter so that the 15-of-16 unmasked
+// tiles run the lean loop: FFMA + MUFU.EX2 + FADD + FMNMX + half an F2FP per element.
+template <typename T, bool kMask>
 __device__ __forceinline__ float softmax_row_pass(uint32_t ts, uint8_t* sP, int row, float scale_log2,
-                                                  float m_off, bool need_mask, int kv0, int limit,
-                                                  float& mx) {
-  float psum = 0.f;
+                                                  float m_off, int kv0, int limit, float& pmax,
+                                                  uint64_t* p_free_bar, uint32_t p_free_parity) {
+  float ps0 = 0.f, ps1 = 0.f, pm0 = 0.f, pm1 = 0.f;
+  const uint32_t prow = row * 128;
+  const uint32_t sw = row & 7;
 #pragma unroll 1
   for (int c = 0; c < kPfN; c += 32) {
     uint32_t r[32];
@@ -71,26 +75,54 @@ __device__ __forceinline__ float softmax_row_pass(uint32_t ts, uint8_t* sP, int 
     uint32_t pk[16];
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-      const float s0 = __uint_as_float(r[i]), s1 = __uint_as_float(r[i + 1]);
-      float p0 = fast_exp2(s0 * scale_log2 - m_off);
-      float p1 = fast_exp2(s1 * scale_log2 - m_off);
-      if (need_mask) {
-        const bool v0 = (kv0 + c + i) <= limit, v1 = (kv0 + c + i + 1) <= limit;
-        p0 = v0 ? p0 : 0.f;
-        p1 = v1 ? p1 : 0.f;
-        mx = fmaxf(mx, fmaxf(v0 ? s0 : -INFINITY, v1 ? s1 : -INFINITY));
-      } else {
-        mx = fmaxf(mx, fmaxf(s0, s1));
+      float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -m_off));
+      float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_off));
+      if constexpr (kMask) {
+        p0 = (kv0 + c + i) <= limit ? p0 : 0.f;
+        p1 = (kv0 + c + i + 1) <= limit ? p1 : 0.f;
       }
-      psum += p0 + p1;
+      ps0 += p0;
+      ps1 += p1;
+      pm0 = fmaxf(pm0, p0);
+      pm1 = fmaxf(pm1, p1);
       pk[i >> 1] = pack2<T>(p0, p1);
     }
+    // the P buffer is still being read by this warpgroup's previous PV: wait as late as possible
+    // (the first 32 exponentials above overlap that MMA)
+    if (c == 0 && p_free_bar != nullptr) mbar_wait(p_free_bar, p_free_parity);
+    // chunks (c/8 .. c/8+3) of this row: all inside one 64-column swizzle block
+    uint8_t* blk = sP + (c >> 6) * 16384 + prow;
+    const uint32_t ch0 = (c >> 3) & 7;
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
-      *reinterpret_cast<uint4*>(sP + tile_off(row, (c >> 3) + ch)) =
+      *reinterpret_cast<uint4*>(blk + (((ch0 + ch) ^ sw) << 4)) =
           make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
   }
-  return psum;
+  pmax = fmaxf(pm0, pm1);
+  return ps0 + ps1;
+}
+
+// max of the visible raw scores of one row of S (TMEM)
+template <bool kMask>
+__device__ __forceinline__ float softmax_row_max(uint32_t ts, int kv0, int limit) {
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < kPfN; c += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(ts + c, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float a = __uint_as_float(r[i]), b = __uint_as_float(r[i + 1]);
+      if constexpr (kMask) {
+        a = (kv0 + c + i) <= limit ? a : -INFINITY;
+        b = (kv0 + c + i + 1) <= limit ? b : -INFINITY;
+      }
+      m0 = fmaxf(m0, a);
+      m1 = fmaxf(m1, b);
+    }
+  }
+  return fmaxf(m0, m1);
 }
 
 template <typename T>
@@ -189,6 +221,13 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
       for (int j = 0; j < n_tiles; ++j) {
         const int g = j & 1, u = j >> 1;
         mbar_wait(&p_full[g], u & 1);
+        // S_{j+2} first when its K tile has already landed: warpgroup g can then start its next
+        // softmax while the tensor core is still busy with PV_j
+        bool s_issued = false;
+        if (j + 2 < n_tiles && mbar_try_wait(&k_full[g], (u + 1) & 1)) {
+          issue_qk(j + 2);
+          s_issued = true;
+        }
         mbar_wait(&v_full[g], u & 1);
         tc_fence_after_sync();
         const uint32_t v_addr = smem_u32(sV + g * kTileBytes);
@@ -204,7 +243,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
         }
         umma_commit(&v_empty[g]);
         umma_commit(&pv_done[g]);
-        if (j + 2 < n_tiles) issue_qk(j + 2);
+        if (j + 2 < n_tiles && !s_issued) issue_qk(j + 2);
       }
     }
   } else if (warp >= 8) {
@@ -263,7 +302,6 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
     uint8_t* myP = sP + g * kTileBytes;
     float m_used = -INFINITY;  // max currently folded into O_g and l (raw score units)
     float l = 0.f;
-    const float thr = kRescaleThreshold / p.scale_log2;
     int u = 0;
     for (int j = g; j < n_tiles; j += 2, ++u) {
       const int kv0 = j * kPfN;
@@ -272,34 +310,29 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
       tc_fence_after_sync();
       if (u == 0) {
         // first tile of this warpgroup: establish the reference max with a max-only pre-pass
-        float mx0 = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < kPfN; c += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(ts + c, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (!need_mask || (kv0 + c + i) <= limit) mx0 = fmaxf(mx0, __uint_as_float(r[i]));
-        }
-        m_used = mx0;
-      } else {
-        // P_g / O_g are free once this warpgroup's previous PV has completed
-        mbar_wait(&pv_done[g], (u - 1) & 1);
-        tc_fence_after_sync();
+        m_used = need_mask ? softmax_row_max<true>(ts, kv0, limit) : softmax_row_max<false>(ts, kv0, limit);
       }
+      // P_g / O_g are free once this warpgroup's previous PV has completed; the pass waits for
+      // that right before its first P store
+      uint64_t* pfree = u > 0 ? &pv_done[g] : nullptr;
+      const uint32_t pfree_par = (u - 1) & 1;
       float m_off = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
-      float mx = -INFINITY;
-      float psum = softmax_row_pass<T>(ts, myP, row, p.scale_log2, m_off, need_mask, kv0, limit, mx);
+      float pmax;
+      float psum = need_mask ? softmax_row_pass<T, true>(ts, myP, row, p.scale_log2, m_off, kv0, limit,
+                                                         pmax, pfree, pfree_par)
+                             : softmax_row_pass<T, false>(ts, myP, row, p.scale_log2, m_off, kv0, limit,
+                                                          pmax, pfree, pfree_par);
       // raise the reference max only when some row outgrew it by > 2^8 (warp-uniform decision:
       // tcgen05.ld/st are warp-collective); then redo the tile against the new max
-      if (__any_sync(0xffffffffu, mx > m_used + thr)) {
+      if (__any_sync(0xffffffffu, pmax > 256.f)) {
+        const float mx = need_mask ? softmax_row_max<true>(ts, kv0, limit) : softmax_row_max<false>(ts, kv0, limit);
         const float m_new = fmaxf(m_used, mx);
         const float alpha = (m_used == -INFINITY) ? 0.f : fast_exp2((m_used - m_new) * p.scale_log2);
         l *= alpha;
         m_used = m_new;
         m_off = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
         if (u > 0) {
+          tc_fence_after_sync();  // PV_{j-2} was observed complete inside the pass
 #pragma unroll 1
           for (int c = 0; c < kPfD; c += 32) {
             uint32_t r[32];
@@ -311,7 +344,10 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
           }
           tmem_st_wait();
         }
-        psum = softmax_row_pass<T>(ts, myP, row, p.scale_log2, m_off, need_mask, kv0, limit, mx);
+        psum = need_mask ? softmax_row_pass<T, true>(ts, myP, row, p.scale_log2, m_off, kv0, limit, pmax,
+                                                     nullptr, 0)
+                         : softmax_row_pass<T, false>(ts, myP, row, p.scale_log2, m_off, kv0, limit, pmax,
+                                                      nullptr, 0);
       }
       l += psum;
       // S_g may be overwritten by S_{j+2}; P_g is ready for PV_j
