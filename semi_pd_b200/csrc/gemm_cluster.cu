@@ -277,7 +277,7 @@ int gemm_cluster_try(void* C, const void* A, const void* W, int64_t M, int64_t N
   int BN = 16;
   while (BN < M) BN <<= 1;
   int S = sms / tiles;            // CTAs per tile that still fit the partition in one wave
-  if (S > 4) S = 4;
+  S = S >= 4 ? 4 : (S >= 2 ? 2 : 1);  // clusters of 3 schedule poorly on the 16-20-SM GPCs (measured)
   if (S > kblocks / 8) S = kblocks / 8;   // >= 8 k-blocks per rank
   const int stage_area = (BN == 16 ? cg_stages<16>() * cg_stage_bytes<16>()
                           : BN == 32 ? cg_stages<32>() * cg_stage_bytes<32>()
