@@ -382,6 +382,7 @@ def main():
             run_window(engine, prompts, dev_prompts, args.output_len, float("inf"), device_resident)
         barrier()
         n0 = _lib._Counter.launches
+        pf0 = engine.prefill.prefill_tokens
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         reqs = []
@@ -395,16 +396,14 @@ def main():
             t = torch.tensor([ms], device=f"cuda:{local_rank}")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, reqs, _lib._Counter.launches - n0
+        return ms, reqs, _lib._Counter.launches - n0, engine.prefill.prefill_tokens - pf0
 
     clocks = ClockSampler(local_rank)
     clocks.start()
-    p0, d0 = engine.prefill.prefill_tokens, engine.decode.decode_tokens
-    ms_dev, _, launches = timed(True, args.steps, args.warmup)
-    prefill_tok = engine.prefill.prefill_tokens - p0
+    ms_dev, _, launches, prefill_tok = timed(True, args.steps, args.warmup)
     # the host-buffer arm repeats the same windows (at most 3 of them, to bound the run time)
     e2e_steps = min(args.steps, 3)
-    ms_e2e, reqs_e2e, _ = timed(False, e2e_steps, 1)
+    ms_e2e, reqs_e2e, _, _ = timed(False, e2e_steps, 1)
     clk = clocks.stop()
 
     out_tokens = args.steps * args.requests * args.output_len * world
