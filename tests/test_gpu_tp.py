@@ -1,0 +1,73 @@
+"""Tensor-parallel forward path on real GPUs (needs >= 2; skipped otherwise): two ranks, NCCL,
+sharded heads / FFN columns, SUM all-reduce after o_proj and down_proj only, vocab-sharded lm_head
+with an all-gather of the logits.  Every rank must reproduce the unsharded CPU
+oracle's logits; decode also runs through the captured CUDA graph (NCCL inside the graph)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=8,
+           num_key_value_heads=4, head_dim=128, vocab_size=2048, max_position_embeddings=2048)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, use_graph, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from oracle import llama_oracle as O
+    from semi_pd_b200.configs import ModelConfig, ServerArgs
+    from semi_pd_b200.model_runner import ModelRunner
+    from tests.helpers import GpuSession
+
+    dtype = torch.float16
+    ocfg = O.OracleLlamaConfig(**CFG)
+    weights = O.make_weights(ocfg, dtype, seed=99)  # identical full checkpoint on every rank
+    sa = ServerArgs(model_path="tp-test", dtype="float16", load_format="external", tp_size=world,
+                    max_total_tokens=2048, max_running_requests=8, context_length=512,
+                    disable_cuda_graph=not use_graph, cuda_graph_bs=[1, 2, 4], enable_semi_pd=True)
+    mr = ModelRunner(ModelConfig(name="tp-test", **CFG), 0.5, rank, rank, world, port, sa)
+    mr.model.load_weights(weights.items())  # each rank keeps its shard
+    mr.init_attention_backend()
+    mr.init_cuda_graphs()
+    assert mr.token_to_kv_pool.head_num == CFG["num_key_value_heads"] // world
+    oracle = O.LlamaOracle(ocfg, weights, kv_slots=2048, max_reqs=9, max_ctx=516, compute="fp32")
+    gs, os_ = GpuSession(mr), O.OracleSession(oracle, 2048, 9)
+    prompts = [[(5 + 3 * i + 17 * j) % CFG["vocab_size"] for i in range(n)] for j, n in enumerate([40, 7, 129])]
+    reqs, lg, ids = gs.extend(prompts)
+    rids, lc, _ = os_.extend(prompts)
+    err = (lg - lc).abs().max().item()
+    tok = lc.argmax(-1).tolist()
+    for _ in range(3):
+        lg, ids = gs.decode(reqs, tok)
+        lc, _ = os_.decode(rids, tok)
+        err = max(err, (lg - lc).abs().max().item())
+        tok = lc.argmax(-1).tolist()
+    ret[rank] = err
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "cuda-graph"])
+def test_tp2_matches_unsharded_oracle(use_graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker, args=(world, port, use_graph, ret), nprocs=world, join=True)
+        errs = dict(ret)
+    assert set(errs) == {0, 1}
+    assert max(errs.values()) < 1e-2, errs
