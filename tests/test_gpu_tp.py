@@ -59,7 +59,9 @@ def _worker(rank, world, port, use_graph, ret):
     torch.distributed.destroy_process_group()
 
 
-@pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "cuda-graph"])
+# NOTE: capturing torch.distributed's NCCL all-reduce inside the decode CUDA graph hung on the pool
+# (round 1); TP decode therefore runs eagerly for now — the graph-safe collective is a §8(f) row.
+@pytest.mark.parametrize("use_graph", [False], ids=["eager"])
 def test_tp2_matches_unsharded_oracle(use_graph):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
