@@ -152,6 +152,11 @@ class ModelRunner:
         self.cuda_graph_runner = None
         if self.server_args.disable_cuda_graph:
             return
+        if self.tp_size > 1:
+            # torch.distributed's NCCL all-reduce captured inside the decode graph hung on the
+            # pool (round 1): TP decode runs eagerly until the graph-safe collective lands
+            logger.warning("TP > 1: decode CUDA graphs disabled")
+            return
         self.cuda_graph_runner = CudaGraphRunner(self)
 
     # ------------------------------------------------------------------------------------------
