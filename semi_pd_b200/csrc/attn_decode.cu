@@ -63,7 +63,7 @@ struct DecodeParams {
 };
 
 struct DcItem {
-  int b, hk, split, t0, t1, n_tiles;
+  int b, hk, split, t0, t1, n_tiles, n_ne;  // n_ne: non-empty splits of this (request, kv head)
 };
 
 __device__ __forceinline__ DcItem dc_item(const DecodeParams& p, const int* s_len, int w) {
@@ -75,6 +75,10 @@ __device__ __forceinline__ DcItem dc_item(const DecodeParams& p, const int* s_le
   const int L = it.b < kDcLenCache ? s_len[it.b] : static_cast<int>(p.seq_lens[it.b]);
   int per = (L + p.splits - 1) / p.splits;
   per = (per + kDcTile - 1) / kDcTile * kDcTile;
+  // a split shorter than two tiles costs more in merge traffic than it saves in streaming time:
+  // short sequences therefore use fewer (non-empty) splits than the launch provides
+  if (p.splits > 1) per = max(per, 2 * kDcTile);
+  it.n_ne = (L + per - 1) / per;
   it.t0 = it.split * per;
   it.t1 = min(L, it.t0 + per);
   it.n_tiles = it.t1 > it.t0 ? (it.t1 - it.t0 + kDcTile - 1) / kDcTile : 0;
@@ -437,7 +441,7 @@ attn_decode_kernel(const DecodeParams p) {
       } else {
 #pragma unroll
         for (int g = 0; g < kDcMaxGroup; ++g)
-          if (g < G) {
+          if (g < G && it.n_tiles > 0) {
             const int64_t idx = (static_cast<int64_t>(it.b) * p.Hq + it.hk * G + g) * p.splits + it.split;
             p.o_part[idx * kDcD + tid] = o[g];
             if (tid == 0) { p.ml_part[idx * 2] = m_ref[g]; p.ml_part[idx * 2 + 1] = l_tot[g]; }
@@ -447,28 +451,36 @@ attn_decode_kernel(const DecodeParams p) {
         if (tid == 0) *flag_slot = atomicAdd(&p.counters[it.b * p.Hk + it.hk], 1);
         softmax_bar();
         if (*flag_slot == p.splits - 1) {
-          // last split of this (request, kv head): merge all partials in split order
+          // last split of this (request, kv head): merge the non-empty partials in split order,
+          // all heads of the group at once so the loads of one split are independent
           __threadfence();
-#pragma unroll 1
-          for (int g = 0; g < G; ++g) {
-            const int64_t base = (static_cast<int64_t>(it.b) * p.Hq + it.hk * G + g) * p.splits;
-            float M = -INFINITY;
-#pragma unroll 4
-            for (int s2 = 0; s2 < p.splits; ++s2) M = fmaxf(M, __ldcg(&p.ml_part[(base + s2) * 2]));
-            float num = 0.f, den = 0.f;
-#pragma unroll 4
-            for (int s2 = 0; s2 < p.splits; ++s2) {
-              const float mm = __ldcg(&p.ml_part[(base + s2) * 2]);
-              const float ll = __ldcg(&p.ml_part[(base + s2) * 2 + 1]);
-              const float ov = __ldcg(&p.o_part[(base + s2) * kDcD + tid]);
-              const float wgt = ll > 0.f ? fast_exp2(mm - M) : 0.f;
-              num += wgt * ov;
-              den += wgt * ll;
-            }
-            reinterpret_cast<T*>(p.out)[it.b * p.out_stride +
-                                        (static_cast<int64_t>(it.hk) * G + g) * kDcD + tid] =
-                from_f32<T>(den > 0.f ? num / den : 0.f);
+          const int64_t base0 = (static_cast<int64_t>(it.b) * p.Hq + it.hk * G) * p.splits;
+          float M[kDcMaxGroup], num[kDcMaxGroup], den[kDcMaxGroup];
+#pragma unroll
+          for (int g = 0; g < kDcMaxGroup; ++g) { M[g] = -INFINITY; num[g] = 0.f; den[g] = 0.f; }
+#pragma unroll 2
+          for (int s2 = 0; s2 < it.n_ne; ++s2)
+#pragma unroll
+            for (int g = 0; g < kDcMaxGroup; ++g)
+              if (g < G) M[g] = fmaxf(M[g], __ldcg(&p.ml_part[(base0 + g * p.splits + s2) * 2]));
+#pragma unroll 2
+          for (int s2 = 0; s2 < it.n_ne; ++s2) {
+#pragma unroll
+            for (int g = 0; g < kDcMaxGroup; ++g)
+              if (g < G) {
+                const int64_t idx = base0 + g * p.splits + s2;
+                const float2 ml = __ldcg(reinterpret_cast<const float2*>(&p.ml_part[idx * 2]));
+                const float ov = __ldcg(&p.o_part[idx * kDcD + tid]);
+                const float wgt = ml.y > 0.f ? fast_exp2(ml.x - M[g]) : 0.f;
+                num[g] += wgt * ov;
+                den[g] += wgt * ml.y;
+              }
           }
+          T* dst = reinterpret_cast<T*>(p.out) + it.b * p.out_stride +
+                   static_cast<int64_t>(it.hk) * G * kDcD + tid;
+#pragma unroll
+          for (int g = 0; g < kDcMaxGroup; ++g)
+            if (g < G) dst[g * kDcD] = from_f32<T>(den[g] > 0.f ? num[g] / den[g] : 0.f);
           if (tid == 0) p.counters[it.b * p.Hk + it.hk] = 0;  // re-arm for the next launch
         }
         softmax_bar();  // flag_slot / red are reused by the next item

@@ -55,9 +55,11 @@ __device__ __forceinline__ float block_sum(float v, float* smem) {
 // (kMaxVec 16-byte vectors per thread) so HBM traffic is exactly 1 read + 1 write per tensor.
 // ------------------------------------------------------------------------------------------------
 constexpr int kNormThreads = 256;
-constexpr int kMaxVec = 8;  // rows up to 256*8*8 = 16384 elements stay in registers
+// kMaxVec is a template parameter (2, 4 or 8: rows up to 4096 / 8192 / 16384 elements stay in
+// registers) so that the common 4096-wide row costs ~40 registers and 8 CTAs fit per SM — the
+// kernel is a pure HBM stream and needs the bytes in flight.
 
-template <typename T, bool kFusedAdd>
+template <typename T, bool kFusedAdd, int kMaxVec>
 __global__ void __launch_bounds__(kNormThreads)
 rmsnorm_kernel(T* out, T* x, T* residual,  // out may alias x (fused variant is in place)
                const T* __restrict__ w, int64_t dim, int64_t x_stride, int64_t out_stride,
@@ -439,10 +441,18 @@ int spd_rmsnorm(void* out, const void* x, const void* w, int64_t tokens, int64_t
                   aligned16(x) && aligned16(w),
               SPD_E_ALIGN, "spd_rmsnorm: dim/strides must be multiples of 8 and pointers 16-B aligned");
   if (tokens == 0) return 0;
+#define SPD_NORM_LAUNCH(FUSED, VEC, ...)                                                         \
+  SPD_CUDA(launch(rmsnorm_kernel<T, FUSED, VEC>, dim3((unsigned)tokens), dim3(kNormThreads), 0, \
+                  as_stream(stream), pdl_enabled(), __VA_ARGS__))
+#define SPD_NORM_DISPATCH(FUSED, ...)                                         \
+  do {                                                                        \
+    if (dim <= 2 * 8 * kNormThreads) SPD_NORM_LAUNCH(FUSED, 2, __VA_ARGS__);  \
+    else if (dim <= 4 * 8 * kNormThreads) SPD_NORM_LAUNCH(FUSED, 4, __VA_ARGS__); \
+    else SPD_NORM_LAUNCH(FUSED, 8, __VA_ARGS__);                              \
+  } while (0)
   SPD_DISPATCH_DTYPE(dtype, {
-    SPD_CUDA(launch(rmsnorm_kernel<T, false>, dim3((unsigned)tokens), dim3(kNormThreads), 0,
-                    as_stream(stream), pdl_enabled(), (T*)out, (T*)x, (T*)nullptr, (const T*)w, dim,
-                    x_stride, out_stride, eps));
+    SPD_NORM_DISPATCH(false, (T*)out, (T*)x, (T*)nullptr, (const T*)w, dim, x_stride, out_stride,
+                      eps);
   });
   return 0;
 }
@@ -455,9 +465,7 @@ int spd_fused_add_rmsnorm(void* x, void* residual, const void* w, int64_t tokens
               "spd_fused_add_rmsnorm: dim must be a multiple of 8 and pointers 16-B aligned");
   if (tokens == 0) return 0;
   SPD_DISPATCH_DTYPE(dtype, {
-    SPD_CUDA(launch(rmsnorm_kernel<T, true>, dim3((unsigned)tokens), dim3(kNormThreads), 0,
-                    as_stream(stream), pdl_enabled(), (T*)x, (T*)x, (T*)residual, (const T*)w, dim,
-                    dim, dim, eps));
+    SPD_NORM_DISPATCH(true, (T*)x, (T*)x, (T*)residual, (const T*)w, dim, dim, dim, eps);
   });
   return 0;
 }

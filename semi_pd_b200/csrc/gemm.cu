@@ -447,6 +447,10 @@ int get_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, u
 int gemm_cluster_try(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_t K, int64_t lda,
                      int64_t ldw, int64_t ldc, int dtype, int out_f32, int sms, cudaStream_t stream);
 
+int gemm_pair_try(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_t K, int64_t lda,
+                  int64_t ldw, int64_t ldc, int dtype, int out_f32, int epilogue, int sms, int panel_mb,
+                  cudaStream_t stream);
+
 constexpr int64_t kGemmWsBytes = 48ll << 20;  // stream-K partials: 2 per CTA
 constexpr int kGemmCounters = 4096;
 
@@ -568,6 +572,10 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
 #undef SPD_GEMM_SWAP
     return set_error(SPD_E_SHAPE, "spd_gemm: unreachable BN=%d", BN);
   }
+
+  // prefill regime proper: 256 x 256 tiles on CTA pairs (tcgen05.mma.cta_group::2, gemm_pair.cu)
+  rc = gemm_pair_try(C, A, W, M, N, K, lda, ldw, ldc, dtype, out_f32, epilogue, sms, env_panel_mb, st);
+  if (rc != 1) return rc;
 
   p.x_rows = M;
   p.y_rows = N;

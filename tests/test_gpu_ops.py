@@ -142,7 +142,11 @@ def test_metadata_exact(ops, bs):
 @pytest.mark.parametrize("M,N,K", [(1, 256, 128), (5, 384, 256), (16, 4096, 4096), (64, 6144, 4096),
                                    (130, 512, 1024), (256, 1024, 14336), (257, 1024, 512),
                                    (1000, 4096, 4096), (1024, 6144, 4096), (384, 28672, 1024),
-                                   (8, 128256, 512), (2048, 264, 1032)])
+                                   (8, 128256, 512), (2048, 264, 1032),
+                                   # CTA-pair (cta_group::2) kernel: exact tiles, N/K tails, M tails
+                                   # incl. a pair tile whose second CTA is entirely out of range
+                                   (512, 256, 64), (768, 1000, 4096), (2500, 776, 328), (2100, 264, 1032),
+                                   (4096, 2048, 512)])
 def test_gemm(ops, dtype, M, N, K):
     """F.linear parity: the oracle is torch CPU matmul of the same 16-bit operands."""
     torch.manual_seed(M + N + K)
@@ -165,6 +169,13 @@ def test_gemm_fused_silu_mul_and_strides(ops, dtype):
     ref = O.silu_and_mul(gu, fp32_math=True).float()
     out = ops.linear(a.to(DEV), w.to(DEV), epilogue=ops.SPD_EPI_SILU_MUL).cpu().float()
     assert (out - ref).abs().max().item() < _tol(dtype, 4e-3, 3e-2)
+    # same through the CTA-pair kernel (M a multiple of 256) and through the single-CTA kernel
+    for M2 in (1024, 640):
+        a2 = (torch.randn(M2, K) * 0.5).to(dtype)
+        gu2 = torch.nn.functional.linear(a2.float(), w.float()).to(dtype)
+        ref2 = O.silu_and_mul(gu2, fp32_math=True).float()
+        out2 = ops.linear(a2.to(DEV), w.to(DEV), epilogue=ops.SPD_EPI_SILU_MUL).cpu().float()
+        assert (out2 - ref2).abs().max().item() < _tol(dtype, 4e-3, 3e-2)
     # strided A (a column slice of a wider activation) and determinism of split-K
     wide = torch.randn(64, 3 * K).to(dtype).to(DEV)
     w2 = (torch.randn(4096, K) / math.sqrt(K)).to(dtype).to(DEV)
