@@ -157,7 +157,9 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
  * The new tokens' K/V must already be in the pool.  q/out: [T, Hq, D], token stride in elements.
  * replaces FlashInferAttnBackend.forward_extend's ragged + paged + merge_state kernels
  * (S/layers/attention/flashinfer_backend.py:386-452); semantics
- * S/layers/attention/torch_native_backend.py:26-109. */
+ * S/layers/attention/torch_native_backend.py:26-109.
+ * sm_budget: SMs of the caller's partition (0 = whole device) — the kernel is persistent, one CTA
+ * per SM. */
 int spd_attn_prefill_ragged(void* out, const void* q, const void* k_pool, const void* v_pool,
                             const int32_t* req_to_token, const int64_t* req_pool_indices,
                             const int32_t* prefix_lens, const int32_t* extend_lens,
@@ -165,7 +167,7 @@ int spd_attn_prefill_ragged(void* out, const void* q, const void* k_pool, const 
                             int64_t max_extend_len, int num_q_heads, int num_kv_heads,
                             int head_dim, int64_t q_stride, int64_t out_stride,
                             int64_t req_to_token_stride, float sm_scale, int dtype,
-                            spd_stream_t stream);
+                            int sm_budget, spd_stream_t stream);
 /* Batched paged-decode attention: one query row per request over its seq_lens[b] cached rows
  * (including the token just written).  Split-KV with an in-kernel merge; workspace from
  * spd_attn_decode_workspace_bytes().  replaces FlashInferAttnBackend.forward_decode

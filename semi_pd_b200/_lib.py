@@ -57,7 +57,7 @@ SIGNATURES = {
     ),
     "spd_attn_prefill_ragged": (
         _i,
-        [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i, _i, _i64, _i64, _i64, _f, _i, _p],
+        [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i, _i, _i64, _i64, _i64, _f, _i, _i, _p],
     ),
     "spd_attn_decode_workspace_bytes": (_i64, [_i64, _i, _i]),
     "spd_attn_decode_paged": (

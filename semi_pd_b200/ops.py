@@ -331,13 +331,15 @@ def attn_prefill(q, k_pool, v_pool, req_to_token, req_pool_indices, prefix_lens,
     for t in (prefix_lens, extend_lens, extend_start_loc):
         if t.dtype != torch.int32:
             raise RuntimeError("attn_prefill: prefix_lens / extend_lens / extend_start_loc must be int32")
-    fn = lib.spd_attn_prefill_ragged if impl == "tc" else lib.spd_attn_prefill_simt
-    check(fn(out.data_ptr(), q2.data_ptr(), k_pool.data_ptr(), v_pool.data_ptr(),
-             req_to_token.data_ptr(), req_pool_indices.data_ptr(), prefix_lens.data_ptr(),
-             extend_lens.data_ptr(), extend_start_loc.data_ptr(), req_pool_indices.numel(), T,
-             int(max_extend_len), num_q_heads, num_kv_heads, head_dim, q2.stride(0), out.stride(0),
-             req_to_token.stride(0), float(sm_scale), _dt(q), _stream()),
-          "spd_attn_prefill_" + impl)
+    args = (out.data_ptr(), q2.data_ptr(), k_pool.data_ptr(), v_pool.data_ptr(),
+            req_to_token.data_ptr(), req_pool_indices.data_ptr(), prefix_lens.data_ptr(),
+            extend_lens.data_ptr(), extend_start_loc.data_ptr(), req_pool_indices.numel(), T,
+            int(max_extend_len), num_q_heads, num_kv_heads, head_dim, q2.stride(0), out.stride(0),
+            req_to_token.stride(0), float(sm_scale), _dt(q))
+    if impl == "tc":
+        check(lib.spd_attn_prefill_ragged(*args, get_sm_budget(), _stream()), "spd_attn_prefill_tc")
+    else:
+        check(lib.spd_attn_prefill_simt(*args, _stream()), "spd_attn_prefill_simt")
     return out
 
 

@@ -56,7 +56,7 @@ def test_argument_errors_are_codes_not_crashes():
     assert lib.spd_attn_decode_paged(p16, p16, p16, p16, p16, p16, p16, 1, 30, 8, 128, 3840, 3840, 8,
                                      0.1, 0, None, 0, 0, None) == -3  # Hq % Hk != 0
     assert lib.spd_attn_prefill_ragged(p16, p16, p16, p16, p16, p16, p16, p16, p16, 1, 8, 8, 8, 2, 96,
-                                       768, 768, 8, 0.1, 0, None) == -3  # head_dim
+                                       768, 768, 8, 0.1, 0, 0, None) == -3  # head_dim
     with pytest.raises(RuntimeError, match="libspd"):
         _lib.check(-1, "demo")
 

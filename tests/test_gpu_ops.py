@@ -231,11 +231,11 @@ def test_attn_decode(ops, impl, dtype, Hq, Hk, lens):
 
 @pytest.mark.parametrize("impl", ["tc", "simt"])
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("Hq,Hk", [(32, 8), (8, 1), (4, 4)])
+@pytest.mark.parametrize("Hq,Hk", [(32, 8), (8, 1), (4, 4), (6, 2)])
 @pytest.mark.parametrize("pre,ext", [([0], [1]), ([0], [128]), ([0, 0], [100, 257]),
                                      ([64, 0, 300], [200, 5, 129]), ([1000], [24]), ([0], [1024]),
-                                     ([127, 128, 129, 1], [1, 1, 127, 130])],
-                         ids=["1tok", "tile", "two", "prefix", "longprefix", "1k", "edges"])
+                                     ([127, 128, 129, 1], [1, 1, 127, 130]), ([0, 40, 0], [700, 1024, 333])],
+                         ids=["1tok", "tile", "two", "prefix", "longprefix", "1k", "edges", "multi"])
 def test_attn_prefill(ops, impl, dtype, Hq, Hk, pre, ext):
     D = 128
     lens = [a + b for a, b in zip(pre, ext)]
@@ -251,6 +251,15 @@ def test_attn_prefill(ops, impl, dtype, Hq, Hk, pre, ext):
                            st, max(ext), Hq, Hk, D, D ** -0.5, impl=impl)
     err = (out.cpu().float().view(-1, Hq, D) - ref.float()).abs().max().item()
     assert err < _tol(dtype, 2e-3, 1.6e-2), err
+    if impl == "tc" and len(ext) > 1:
+        # the persistent kernel on a small SM budget: every CTA walks many items back to back
+        ops.set_sm_budget(8)
+        try:
+            out8 = ops.attn_prefill(q.to(DEV).view(T, -1), kp.to(DEV), vp.to(DEV), rtt.to(DEV), rpi.to(DEV), pre_t,
+                                    ext_t, st, max(ext), Hq, Hk, D, D ** -0.5, impl=impl)
+        finally:
+            ops.set_sm_budget(0)
+        assert torch.equal(out8, out)  # the schedule must not change a single bit
 
 
 def test_attention_on_reference_golden_vectors(ops, golden):
