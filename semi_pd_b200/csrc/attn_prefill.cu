@@ -13,20 +13,25 @@
 // K/V tile staged once in shared memory feeds 2 x 128 query rows (half the L2->SM traffic per
 // FLOP of a single-tile CTA) and the tensor core alternates between the two warpgroups: while
 // warpgroup 0 exponentiates S0_j the tensor core runs PV1_{j-1} / S1_j, and vice versa.
-// Roles (448 threads):
+// Roles (384 threads):
 //   warps 0-3 / 4-7  softmax warpgroup 0 / 1: one thread per query row, ONE pass per tile in the
 //                    exp2 domain against a lazily raised reference max (O in TMEM is rescaled only
-//                    when a row outgrows it by 2^8 — then the tile is redone; rare after tile 0);
+//                    when a row outgrows it by 2^8 — then the tile is redone; rare after tile 0).
+//                    P never touches shared memory: the 16-bit probabilities are written back
+//                    into TMEM over the first 64 columns of the S tile they came from
+//                    (tcgen05.st) and feed the PV MMA as its A operand from TMEM;
 //                    epilogue O / l straight from TMEM to global memory;
-//   warps 8-9, 10-11 K / V loaders: gather rows through req_to_token with 16-byte cp.async into
-//                    128-byte-swizzled smem; one 3-slot ring K_j V_j K_{j+1} ... runs ahead of the
+//   warp 8, warp 9   K / V loader: gather rows through req_to_token with 16-byte cp.async into
+//                    128-byte-swizzled smem; one 5-slot ring K_j V_j K_{j+1} ... runs ahead of the
 //                    consumer ACROSS items, so an item's first tiles are in flight while the
 //                    previous item drains;
-//   warp 12          MMA issuer: S_w = Q_w K_j^T (K-major), O_w += P_w V_j (V MN-major);
-//   warp 13          Q loader (TMA): the next item's Q tiles are fetched as soon as the current
+//   warp 10          MMA issuer: S_w = Q_w K_j^T (both K-major in smem), O_w += P_w V_j (P from
+//                    TMEM, V MN-major in smem); per warpgroup the order is PV_j then S_{j+1}
+//                    (S_{j+1} overwrites the columns P_j lives in; tcgen05.mma executes in order);
+//   warp 11          Q loader (TMA): the next item's Q tiles are fetched as soon as the current
 //                    item's last S MMA has read them.
 // Items are ordered heaviest (latest query tiles) first and dealt to the CTAs in snake order.
-// smem: Q0 Q1 P0 P1 + 3 K/V slots = 7 x 32 KB.  TMEM: S0 | S1 | O0 | O1 = 512 columns.
+// smem: Q0 Q1 + 5 K/V slots = 7 x 32 KB.  TMEM: S0/P0 | S1/P1 | O0 | O1 = 512 columns.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -35,13 +40,13 @@
 
 namespace spd {
 
-constexpr int kPfThreads = 448;
+constexpr int kPfThreads = 384;  // 12 warps -> 168 registers per thread for the softmax warps
 constexpr int kPfM = 128;    // query rows per warpgroup tile
 constexpr int kPfN = 128;    // kv tokens per tile
 constexpr int kPfD = 128;    // head dim
 constexpr int kTileBytes = 128 * 128 * 2;  // one [128 x 128] 16-bit tile = two 16 KB swizzle blocks
-constexpr int kPfSlots = 3;
-constexpr int kPfSmem = kTileBytes * (4 + kPfSlots) + 1024 + 512;
+constexpr int kPfSlots = 5;
+constexpr int kPfSmem = kTileBytes * (2 + kPfSlots) + 1024 + 512;
 constexpr float kRescaleTrigger = 256.f;  // a row sum above 2^8 may hide an element above 2^8
 
 struct PrefillParams {
@@ -114,68 +119,89 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk16) {
   return (chunk16 >> 3) * 16384 + row * 128 + (((chunk16 & 7) ^ (row & 7)) << 4);
 }
 
-// One tile row for one thread: S (TMEM) -> p = exp2(s*scale - m_off) -> P (smem, 16-bit).
-// Returns the row sum of p (masked entries excluded).  kMask is a template parameter so that the
-// unmasked tiles run the lean loop: FFMA + MUFU.EX2 + FADD + half an F2FP per element.
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (here the 16-bit probabilities, two per 32-bit
+// column, row = TMEM lane) is read from tensor memory
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 32 columns of one tile row: p = exp2(s*scale - m_off), packed to 16 bits into pk[0..16)
 template <typename T, bool kMask>
-__device__ __forceinline__ float softmax_row_pass(uint32_t ts, uint8_t* sP, int row, float scale_log2,
-                                                  float m_off, int kv0, int limit,
-                                                  uint64_t* p_free_bar, uint32_t p_free_parity) {
-  float ps0 = 0.f, ps1 = 0.f;
-  const uint32_t prow = row * 128;
-  const uint32_t sw = row & 7;
-#pragma unroll 1
-  for (int c = 0; c < kPfN; c += 32) {
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(ts + c, r);
-    tmem_ld_wait();
-    uint32_t pk[16];
+__device__ __forceinline__ void softmax_chunk(const uint32_t* r, int c, uint32_t* pk, float scale_log2,
+                                              float m_off, int kv0, int limit, float& ps0, float& ps1) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -m_off));
-      float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_off));
-      if constexpr (kMask) {
-        p0 = (kv0 + c + i) <= limit ? p0 : 0.f;
-        p1 = (kv0 + c + i + 1) <= limit ? p1 : 0.f;
-      }
-      ps0 += p0;
-      ps1 += p1;
-      pk[i >> 1] = pack2<T>(p0, p1);
+  for (int i = 0; i < 32; i += 2) {
+    float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -m_off));
+    float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_off));
+    if constexpr (kMask) {
+      p0 = (kv0 + c + i) <= limit ? p0 : 0.f;
+      p1 = (kv0 + c + i + 1) <= limit ? p1 : 0.f;
     }
-    // the P buffer is still being read by this warpgroup's previous PV: wait as late as possible
-    // (the first 32 exponentials above overlap that MMA)
-    if (c == 0 && p_free_bar != nullptr) mbar_wait(p_free_bar, p_free_parity);
-    // chunks (c/8 .. c/8+3) of this row: all inside one 64-column swizzle block
-    uint8_t* blk = sP + (c >> 6) * 16384 + prow;
-    const uint32_t ch0 = (c >> 3) & 7;
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch)
-      *reinterpret_cast<uint4*>(blk + (((ch0 + ch) ^ sw) << 4)) =
-          make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+    ps0 += p0;
+    ps1 += p1;
+    pk[i >> 1] = pack2<T>(p0, p1);
   }
+}
+
+// One tile row for one thread: S (TMEM) -> 64 packed 16-bit pairs in registers.  Returns the row
+// sum of p (masked entries excluded).  The TMEM loads are software-pipelined (the next 32 columns
+// are in flight while the current 32 are exponentiated): with one softmax warp per scheduler
+// nothing else hides the tcgen05.ld latency.  kMask is a template parameter so that the unmasked
+// tiles run the lean loop: FFMA + MUFU.EX2 + FADD + half an F2FP per element.
+template <typename T, bool kMask>
+__device__ __forceinline__ float softmax_row_pass(uint32_t ts, uint32_t* pk, float scale_log2, float m_off,
+                                                  int kv0, int limit) {
+  float ps0 = 0.f, ps1 = 0.f;
+  uint32_t ra[32], rb[32];
+  tmem_ld_32x32b_x32(ts, ra);
+  tmem_ld_wait();
+  tmem_ld_32x32b_x32(ts + 32, rb);
+  softmax_chunk<T, kMask>(ra, 0, pk, scale_log2, m_off, kv0, limit, ps0, ps1);
+  tmem_ld_wait();
+  tmem_ld_32x32b_x32(ts + 64, ra);
+  softmax_chunk<T, kMask>(rb, 32, pk + 16, scale_log2, m_off, kv0, limit, ps0, ps1);
+  tmem_ld_wait();
+  tmem_ld_32x32b_x32(ts + 96, rb);
+  softmax_chunk<T, kMask>(ra, 64, pk + 32, scale_log2, m_off, kv0, limit, ps0, ps1);
+  tmem_ld_wait();
+  softmax_chunk<T, kMask>(rb, 96, pk + 48, scale_log2, m_off, kv0, limit, ps0, ps1);
   return ps0 + ps1;
 }
 
 // max of the visible raw scores of one row of S (TMEM)
 template <bool kMask>
+__device__ __forceinline__ void rowmax_chunk(const uint32_t* r, int c, int kv0, int limit, float& m0, float& m1) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float a = __uint_as_float(r[i]), b = __uint_as_float(r[i + 1]);
+    if constexpr (kMask) {
+      a = (kv0 + c + i) <= limit ? a : -INFINITY;
+      b = (kv0 + c + i + 1) <= limit ? b : -INFINITY;
+    }
+    m0 = fmaxf(m0, a);
+    m1 = fmaxf(m1, b);
+  }
+}
+template <bool kMask>
 __device__ __forceinline__ float softmax_row_max(uint32_t ts, int kv0, int limit) {
   float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < kPfN; c += 32) {
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(ts + c, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      float a = __uint_as_float(r[i]), b = __uint_as_float(r[i + 1]);
-      if constexpr (kMask) {
-        a = (kv0 + c + i) <= limit ? a : -INFINITY;
-        b = (kv0 + c + i + 1) <= limit ? b : -INFINITY;
-      }
-      m0 = fmaxf(m0, a);
-      m1 = fmaxf(m1, b);
-    }
-  }
+  uint32_t ra[32], rb[32];
+  tmem_ld_32x32b_x32(ts, ra);
+  tmem_ld_32x32b_x32(ts + 32, rb);
+  tmem_ld_wait();
+  rowmax_chunk<kMask>(ra, 0, kv0, limit, m0, m1);
+  tmem_ld_32x32b_x32(ts + 64, ra);
+  rowmax_chunk<kMask>(rb, 32, kv0, limit, m0, m1);
+  tmem_ld_32x32b_x32(ts + 96, rb);
+  tmem_ld_wait();
+  rowmax_chunk<kMask>(ra, 64, kv0, limit, m0, m1);
+  rowmax_chunk<kMask>(rb, 96, kv0, limit, m0, m1);
   return fmaxf(m0, m1);
 }
 
@@ -186,35 +212,32 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                     // 2 tiles (warpgroup 0 / 1)
-  uint8_t* sP = smem + 2 * kTileBytes;    // 2 tiles
-  uint8_t* sKV = smem + 4 * kTileBytes;   // ring: position 2t = K of tile t, 2t+1 = V of tile t
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (4 + kPfSlots) * kTileBytes);
-  uint64_t* q_full = bars;            // 1
-  uint64_t* q_empty = bars + 1;       // 1
-  uint64_t* kv_full = bars + 2;       // kPfSlots
-  uint64_t* kv_empty = bars + 5;      // kPfSlots
-  uint64_t* s_full = bars + 8;        // 2 (per warpgroup)
-  uint64_t* s_empty = bars + 10;      // 2
-  uint64_t* p_full = bars + 12;       // 2
-  uint64_t* pv_done = bars + 14;      // 2
-  uint64_t* o_free = bars + 16;       // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint8_t* sKV = smem + 2 * kTileBytes;   // ring: position 2t = K of tile t, 2t+1 = V of tile t
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + kPfSlots) * kTileBytes);
+  uint64_t* q_full = bars;                     // 1
+  uint64_t* q_empty = bars + 1;                // 1
+  uint64_t* kv_full = bars + 2;                // kPfSlots
+  uint64_t* kv_empty = kv_full + kPfSlots;     // kPfSlots
+  uint64_t* s_full = kv_empty + kPfSlots;      // 2 (per warpgroup)
+  uint64_t* p_full = s_full + 2;               // 2
+  uint64_t* pv_done = p_full + 2;              // 2
+  uint64_t* o_free = pv_done + 2;              // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cta = blockIdx.x, ncta = gridDim.x;
 
-  if (warp == 12) {
+  if (warp == 10) {
     if (lane == 0) {
       mbar_init(q_full, 1);
       mbar_init(q_empty, 1);
       for (int i = 0; i < kPfSlots; ++i) {
-        mbar_init(&kv_full[i], 64);
+        mbar_init(&kv_full[i], 32);
         mbar_init(&kv_empty[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
-        mbar_init(&s_empty[i], 4);
         mbar_init(&p_full[i], 4);
         mbar_init(&pv_done[i], 1);
         mbar_init(&o_free[i], 4);
@@ -225,17 +248,17 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  if (warp == 13 && lane == 0) tma_prefetch_desc(&tmQ);
+  if (warp == 11 && lane == 0) tma_prefetch_desc(&tmQ);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns (warpgroup 0 / 1)
+  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns (warpgroup 0 / 1); P aliases cols 0..63
   const uint32_t tmem_O = tmem_base + 256;  // 2 x 128 columns
 
   griddep_wait();
 
-  if (warp == 13) {
+  if (warp == 11) {
     // ===================== Q loader =====================
     if (elect_one()) {
       uint32_t itn = 0;
@@ -256,13 +279,12 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
         ++itn;
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == 10) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc<T>(kPfM, kPfN, 0, 0);  // A, B K-major
-      constexpr uint32_t idesc_pv = umma_idesc<T>(kPfM, kPfD, 0, 1);  // B (V) MN-major
+      constexpr uint32_t idesc_pv = umma_idesc<T>(kPfM, kPfD, 0, 1);  // A = P (TMEM), B = V MN-major
       uint32_t t_base = 0;          // tiles of all previous items (ring position / 2)
-      uint32_t sq[2] = {0, 0};      // S tiles issued per warpgroup (all items)
       uint32_t pq[2] = {0, 0};      // PV tiles issued per warpgroup (all items)
       uint32_t eq[2] = {0, 0};      // items per warpgroup (o_free phase)
       uint32_t itn = 0;
@@ -272,17 +294,11 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
         const PfItem it = pf_item(p, idx);
         if (it.n == 0) continue;
         mbar_wait(q_full, itn & 1);
-        auto k_ready = [&](int j, bool block) -> bool {
+        // S_w(j): the warpgroup's previous P (aliasing S) has been consumed by PV_{j-1}, issued
+        // earlier by this thread — tcgen05.mma executes in issue order
+        auto issue_s = [&](int w, int j) {
           const uint32_t pos = 2 * (t_base + j);
-          if (block) {
-            mbar_wait(&kv_full[pos % kPfSlots], (pos / kPfSlots) & 1);
-            return true;
-          }
-          return mbar_try_wait(&kv_full[pos % kPfSlots], (pos / kPfSlots) & 1);
-        };
-        auto issue_s = [&](int w, int j) {  // K_j is known to be resident
-          const uint32_t pos = 2 * (t_base + j);
-          mbar_wait(&s_empty[w], (sq[w] & 1) ^ 1);
+          mbar_wait(&kv_full[pos % kPfSlots], (pos / kPfSlots) & 1);
           tc_fence_after_sync();
           const uint32_t q_addr = smem_u32(sQ + w * kTileBytes);
           const uint32_t k_addr = smem_u32(sKV + (pos % kPfSlots) * kTileBytes);
@@ -293,7 +309,6 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
                     umma_desc_sw128(k_addr + off, 16, 1024), idesc_qk, k > 0 ? 1u : 0u);
           }
           umma_commit(&s_full[w]);
-          ++sq[w];
         };
         // after the S MMAs of tile j (both warpgroups) have been issued: release K_j, and Q after
         // the item's last S
@@ -301,49 +316,37 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
           umma_commit(&kv_empty[(2 * (t_base + j)) % kPfSlots]);
           if (j == it.n - 1) umma_commit(q_empty);
         };
-        k_ready(0, true);
 #pragma unroll
         for (int w = 0; w < 2; ++w)
-          if (it.nt[w] > 0) issue_s(w, 0);
+          if (it.nt[w] > 0) {
+            // the epilogue of the previous item reads O, not S — but its last PV (reading P in the
+            // S columns) was issued before this S, so S_0 may go out immediately
+            issue_s(w, 0);
+          }
         s_tile_issued(0);
         for (int j = 0; j < it.n; ++j) {
           const uint32_t vpos = 2 * (t_base + j) + 1;
-          int s_next_issued = 0;
 #pragma unroll
           for (int w = 0; w < 2; ++w) {
             if (j >= it.nt[w]) continue;
             mbar_wait(&p_full[w], pq[w] & 1);
-            // S_{j+1} first when its K tile has already landed: the warpgroup can then start its
-            // next softmax while the tensor core is still busy with PV_j
-            bool s_issued = false;
-            if (j + 1 < it.nt[w] && k_ready(j + 1, false)) {
-              issue_s(w, j + 1);
-              s_issued = true;
-            }
             mbar_wait(&kv_full[vpos % kPfSlots], (vpos / kPfSlots) & 1);
             if (j == 0) mbar_wait(&o_free[w], (eq[w] & 1) ^ 1);  // previous item's O has been read
             tc_fence_after_sync();
             const uint32_t v_addr = smem_u32(sKV + (vpos % kPfSlots) * kTileBytes);
-            const uint32_t p_addr = smem_u32(sP + w * kTileBytes);
 #pragma unroll
             for (int k = 0; k < kPfN / 16; ++k) {
-              // A = P[128 x 16 kv] (K-major), B = V[16 kv x 128 d] (MN-major: 2 blocks of 64 d,
-              // LBO = 16 KB; kv rows 128 B apart, 8-row groups SBO = 1 KB)
-              const uint32_t a_off = (k >> 2) * 16384 + (k & 3) * 32;
-              umma_ss(tmem_O + w * kPfD, umma_desc_sw128(p_addr + a_off, 16, 1024),
+              // A = P[128 x 16 kv]: 8 TMEM columns per k-step; B = V[16 kv x 128 d] (MN-major: 2
+              // blocks of 64 d, LBO = 16 KB; kv rows 128 B apart, 8-row groups SBO = 1 KB)
+              umma_ts(tmem_O + w * kPfD, tmem_S + w * kPfN + k * 8,
                       umma_desc_sw128(v_addr + k * 2048, 16384, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
             }
             umma_commit(&pv_done[w]);
             ++pq[w];
-            if (j + 1 < it.nt[w] && !s_issued) {
-              k_ready(j + 1, true);
-              issue_s(w, j + 1);
-            }
-            if (j + 1 < it.nt[w]) ++s_next_issued;
+            if (j + 1 < it.nt[w]) issue_s(w, j + 1);
           }
           umma_commit(&kv_empty[vpos % kPfSlots]);  // V_j: both PVs issued
           if (j + 1 < it.n) s_tile_issued(j + 1);
-          (void)s_next_issued;
         }
 #pragma unroll
         for (int w = 0; w < 2; ++w)
@@ -353,15 +356,14 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
       }
     }
   } else if (warp >= 8) {
-    // ===================== K loaders (warps 8-9) / V loaders (warps 10-11) =====================
-    const int is_v = warp >= 10 ? 1 : 0;
-    const int lt = (threadIdx.x - 256) & 63;
-    const int chunk = lt & 15;   // 16-byte chunk of the 256-byte head row
-    const int rsub = lt >> 4;    // 0..3
+    // ===================== K loader (warp 8) / V loader (warp 9) =====================
+    const int is_v = warp == 9 ? 1 : 0;
+    const int chunk = lane & 15;   // 16-byte chunk of the 256-byte head row
+    const int rsub = lane >> 4;    // 0..1
     const T* pool = reinterpret_cast<const T*>(is_v ? p.v_pool : p.k_pool);
     const int64_t row_elems = static_cast<int64_t>(p.Hk) * kPfD;
     uint32_t t = 0;        // tiles loaded so far (all items)
-    int pending = -1;      // slot whose cp.async group has been committed but not yet published
+    int pending = -1;      // slot whose cp.async group is committed but not yet published
     for (int k = 0;; ++k) {
       const int idx = pf_rank(k, cta, ncta);
       if (idx >= p.total_items) break;
@@ -370,34 +372,43 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
       const int32_t* rtt = p.req_to_token + p.req_pool_indices[it.req] * p.rtt_stride;
       const int64_t col = static_cast<int64_t>(it.hk) * kPfD + chunk * 8;
       for (int j = 0; j < it.n; ++j, ++t) {
-        // page-table lookups first, all in flight together and overlapped with the waits below (the
-        // cp.async asm is a compiler barrier; interleaving the lookups with it would serialise the
-        // dependent global-load latencies)
-        int slot[32];
+        // page-table lookups first, all in flight together (the cp.async asm is a compiler
+        // barrier; interleaving the lookups with it would serialise the dependent load latencies)
+        int slot[64];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kv = j * kPfN + i * 4 + rsub;
+        for (int i = 0; i < 64; ++i) {
+          const int kv = j * kPfN + i * 2 + rsub;
           slot[i] = kv < it.kv_len ? __ldg(rtt + kv) : -1;
-        }
-        // publish the previous tile BEFORE waiting for this tile's slot (the consumer of the
-        // previous tile must never wait on a producer that waits on the consumer)
-        if (pending >= 0) {
-          cp_async_wait<0>();
-          fence_proxy_async_smem();
-          mbar_arrive(&kv_full[pending]);
         }
         const uint32_t pos = 2 * t + is_v;
         const int st = pos % kPfSlots;
-        mbar_wait(&kv_empty[st], ((pos / kPfSlots) & 1) ^ 1);
+        const uint32_t epar = ((pos / kPfSlots) & 1) ^ 1;
+        // Keep two tiles in flight when the ring has room.  If this tile's slot is still in use,
+        // publish the previous tile BEFORE blocking on the slot: the consumer of the previous
+        // tile must never wait on a producer that waits on the consumer.
+        bool publish_after = true;
+        if (pending >= 0 && !mbar_try_wait(&kv_empty[st], epar)) {
+          cp_async_wait<0>();
+          fence_proxy_async_smem();
+          mbar_arrive(&kv_full[pending]);
+          pending = -1;
+          publish_after = false;
+        }
+        mbar_wait(&kv_empty[st], epar);
         const uint32_t dst = smem_u32(sKV + st * kTileBytes);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int row = i * 4 + rsub;
+        for (int i = 0; i < 64; ++i) {
+          const int row = i * 2 + rsub;
           const bool valid = slot[i] >= 0;
           const int64_t s64 = valid ? slot[i] : 0;
           cp_async16(dst + tile_off(row, chunk), pool + s64 * row_elems + col, valid);
         }
         cp_async_commit();
+        if (publish_after && pending >= 0) {
+          cp_async_wait<1>();  // everything but the group just committed has landed
+          fence_proxy_async_smem();
+          mbar_arrive(&kv_full[pending]);
+        }
         pending = st;
       }
     }
@@ -413,37 +424,36 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t ts = tmem_S + lane_base + w * kPfN;
     const uint32_t to = tmem_O + lane_base + w * kPfD;
-    uint8_t* myP = sP + w * kTileBytes;
     uint32_t u = 0;  // tiles processed by this warpgroup (all items)
     for (int k = 0;; ++k) {
       const int idx = pf_rank(k, cta, ncta);
       if (idx >= p.total_items) break;
       const PfItem it = pf_item(p, idx);
-      if (it.nt[w] == 0) continue;
-      const int limit = it.pre + it.m0[w] + row;  // last visible key of this row (causal)
+      const int nt = w == 0 ? it.nt[0] : it.nt[1];
+      if (nt == 0) continue;
+      const int m0 = w == 0 ? it.m0[0] : it.m0[1];
+      const int rows_valid = w == 0 ? it.rows[0] : it.rows[1];
+      const int head = w == 0 ? it.head[0] : it.head[1];
+      const int q_row0 = w == 0 ? it.q_row0[0] : it.q_row0[1];
+      const int limit = it.pre + m0 + row;  // last visible key of this row (causal)
       float m_used = -INFINITY;  // max currently folded into O and l (raw score units)
       float l = 0.f;
-      for (int j = 0; j < it.nt[w]; ++j, ++u) {
+      for (int j = 0; j < nt; ++j, ++u) {
         const int kv0 = j * kPfN;
-        const bool need_mask = (kv0 + kPfN - 1) > (it.pre + it.m0[w]);
+        const bool need_mask = (kv0 + kPfN - 1) > (it.pre + m0);
         mbar_wait(&s_full[w], u & 1);
         tc_fence_after_sync();
         if (j == 0) {
           // first tile of the item: establish the reference max with a max-only pre-pass
           m_used = need_mask ? softmax_row_max<true>(ts, kv0, limit) : softmax_row_max<false>(ts, kv0, limit);
         }
-        // P / O are free once this warpgroup's previous PV has completed; the pass waits for that
-        // right before its first P store (the previous item's last PV was awaited by its epilogue)
-        uint64_t* pfree = j > 0 ? &pv_done[w] : nullptr;
-        const uint32_t pfree_par = (u - 1) & 1;
         float m_off = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
-        float psum = need_mask ? softmax_row_pass<T, true>(ts, myP, row, p.scale_log2, m_off, kv0, limit,
-                                                           pfree, pfree_par)
-                               : softmax_row_pass<T, false>(ts, myP, row, p.scale_log2, m_off, kv0, limit,
-                                                            pfree, pfree_par);
+        uint32_t pk[64];
+        float psum = need_mask ? softmax_row_pass<T, true>(ts, pk, p.scale_log2, m_off, kv0, limit)
+                               : softmax_row_pass<T, false>(ts, pk, p.scale_log2, m_off, kv0, limit);
         // raise the reference max only when some row may have outgrown it by > 2^8 (an element
         // above 2^8 implies a row sum above 2^8; warp-uniform decision: tcgen05.ld/st are
-        // warp-collective); then redo the tile against the new max
+        // warp-collective); S is still intact (P is stored below), so the tile is simply redone
         if (__any_sync(0xffffffffu, psum > kRescaleTrigger)) {
           const float mx = need_mask ? softmax_row_max<true>(ts, kv0, limit) : softmax_row_max<false>(ts, kv0, limit);
           const float m_new = fmaxf(m_used, mx);
@@ -452,7 +462,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
           m_used = m_new;
           m_off = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
           if (j > 0) {
-            tc_fence_after_sync();  // PV_{j-1} was observed complete inside the pass
+            // S_j was issued after PV_{j-1}: O is complete up to tile j-1
 #pragma unroll 1
             for (int c = 0; c < kPfD; c += 32) {
               uint32_t r[32];
@@ -462,27 +472,25 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
               for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
               tmem_st_32x32b_x32(to + c, r);
             }
-            tmem_st_wait();
           }
-          psum = need_mask ? softmax_row_pass<T, true>(ts, myP, row, p.scale_log2, m_off, kv0, limit, nullptr, 0)
-                           : softmax_row_pass<T, false>(ts, myP, row, p.scale_log2, m_off, kv0, limit, nullptr, 0);
+          psum = need_mask ? softmax_row_pass<T, true>(ts, pk, p.scale_log2, m_off, kv0, limit)
+                           : softmax_row_pass<T, false>(ts, pk, p.scale_log2, m_off, kv0, limit);
         }
         l += psum;
-        // S may be overwritten by S_{j+1}; P is ready for PV_j
-        fence_proxy_async_smem();
+        // P_j over the first 64 columns of S_j (every column of S_j is in registers by now)
+        tmem_st_32x32b_x32(ts, pk);
+        tmem_st_32x32b_x32(ts + 32, pk + 32);
+        tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&s_empty[w]);
-          mbar_arrive(&p_full[w]);
-        }
+        if (lane == 0) mbar_arrive(&p_full[w]);
       }
       // ---- epilogue: O / l, TMEM -> registers -> global ----
       mbar_wait(&pv_done[w], (u - 1) & 1);
       tc_fence_after_sync();
       const float inv_l = l > 0.f ? 1.f / l : 0.f;
-      T* dst = reinterpret_cast<T*>(p.out) + static_cast<int64_t>(it.q_row0[w] + row) * p.out_stride +
-               static_cast<int64_t>(it.head[w]) * kPfD;
+      T* dst = reinterpret_cast<T*>(p.out) + static_cast<int64_t>(q_row0 + row) * p.out_stride +
+               static_cast<int64_t>(head) * kPfD;
 #pragma unroll 1
       for (int c = 0; c < kPfD; c += 64) {
         uint32_t a[32], b[32];
@@ -495,7 +503,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
           __syncwarp();
           if (lane == 0) mbar_arrive(&o_free[w]);
         }
-        if (row < it.rows[w]) {
+        if (row < rows_valid) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             uint4 v;
@@ -522,7 +530,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
   griddep_launch_dependents();
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 12) tmem_dealloc(tmem_base, 512);
+  if (warp == 10) tmem_dealloc(tmem_base, 512);
 }
 
 int check_attn_args(const char* fn, const void* out, const void* q, const void* k_pool,
