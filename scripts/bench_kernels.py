@@ -1,6 +1,7 @@
 """Kernel micro-benchmarks at Llama-3-8B decode/prefill shapes, timed as CUDA-graph replays of N
 back-to-back launches (no Python launch overhead), L2 flushed by the working set itself
-(distinct weight buffers per launch).  usage: python scripts/bench_kernels.py [sm_budget]"""
+(distinct weight buffers per launch).  usage: python scripts/bench_kernels.py [sm_budget] [sections=gd,ad,ap,gp]
+(gd = decode-regime GEMMs, ad = decode attention, ap = prefill attention, gp = prefill-regime GEMMs)"""
 import sys
 
 import torch
@@ -11,6 +12,7 @@ from semi_pd_b200 import ops  # noqa: E402
 dev = torch.device("cuda:0")
 budget = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 ops.set_sm_budget(budget)
+sections = (sys.argv[2] if len(sys.argv) > 2 else "gd,ad,ap,gp").split(",")
 torch.manual_seed(0)
 
 
@@ -38,7 +40,7 @@ def graph_time(fns, reps=5):
 
 
 print(f"== decode-regime GEMMs (sm_budget={budget or 'all'}) ==")
-for M in (1, 16, 64, 128, 160):
+for M in ((1, 16, 64, 128, 160, 192) if "gd" in sections else ()):
     for (N, K, name) in ((6144, 4096, "qkv"), (4096, 4096, "o"), (28672, 4096, "gate_up"), (4096, 14336, "down"),
                          (128256, 4096, "lm_head")):
         nbuf = 3 if N > 100000 else 8
@@ -54,7 +56,8 @@ for M in (1, 16, 64, 128, 160):
 
 print("== decode attention ==")
 Hq, Hk, D = 32, 8, 128
-for (B, S) in ((1, 1088), (8, 1088), (32, 1088), (64, 1088), (128, 1088), (160, 1088), (16, 8192)):
+for (B, S) in (((1, 1088), (8, 1088), (32, 1088), (64, 1088), (128, 1088), (160, 1088), (16, 8192), (64, 300))
+               if "ad" in sections else ()):
     slots = B * S + 8
     nb = 4
     kps = [torch.randn(slots, Hk, D, device=dev).bfloat16() for _ in range(nb)]
@@ -72,7 +75,7 @@ for (B, S) in ((1, 1088), (8, 1088), (32, 1088), (64, 1088), (128, 1088), (160, 
     del kps, vps
 
 print("== prefill attention ==")
-for (nreq, E, P) in ((1, 1024, 0), (8, 1024, 0), (2, 4096, 0), (4, 1024, 3072)):
+for (nreq, E, P) in (((1, 1024, 0), (8, 1024, 0), (2, 4096, 0), (4, 1024, 3072)) if "ap" in sections else ()):
     L = E + P
     slots = nreq * L + 8
     kp = torch.randn(slots, Hk, D, device=dev).bfloat16()
@@ -89,7 +92,7 @@ for (nreq, E, P) in ((1, 1024, 0), (8, 1024, 0), (2, 4096, 0), (4, 1024, 3072)):
     print(f"  {nreq} x {E} (+{P} prefix): {ms*1e3:7.1f} us {fl/ms/1e9:6.1f} TF/s", flush=True)
 
 print("== prefill-regime GEMMs ==")
-for M in (1024, 8192):
+for M in ((1024, 8192) if "gp" in sections else ()):
     for (N, K, name, epi) in ((6144, 4096, "qkv", 0), (4096, 4096, "o", 0), (14336, 4096, "gate_up+silu", 1),
                               (4096, 14336, "down", 0)):
         w = torch.randn(N * (2 if epi else 1), K, device=dev).bfloat16()

@@ -23,8 +23,14 @@
 // kept per thread and reduced once per item.  Raising m_ref (always on an item's first tile,
 // rarely afterwards) takes the slow path: true tile max via shuffles, O^T rescaled in TMEM.
 //
-// warps 0-3: softmax, O rescale, epilogue     warps 4-7: K/V gather through req_to_token (16-byte
-// cp.async, 128-byte swizzle) + Q staging     warp 8: MMA issuer + TMEM allocator
+// warps 0-3: softmax, O rescale, epilogue     warps 4-5 / 6-7: K / V gather through req_to_token
+// (16-byte cp.async, 128-byte swizzle; separate 3-slot rings) + Q staging     warp 8: MMA issuer +
+// TMEM allocator.
+// Why cp.async and not TMA: the pool is token-granular, so a tile is 128 scattered 256-byte rows.
+// tile::gather4 (4 rows x 128 B per instruction) was built and measured on B200: correct (the
+// swizzle and the zero fill of out-of-range rows match, scripts/probes/gather4_probe.cu) but the
+// TMA unit retires only ~1 such instruction per 27 clk -> 36 GB/s per SM against 47 GB/s for this
+// cp.async gather (profiles/r01_decode_attention_loader_experiments.md).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -40,8 +46,9 @@ constexpr int kDcStages = 3;
 constexpr int kDcTileBytes = 128 * 128 * 2;
 constexpr int kDcQBytes = 16 * 128 * 2;   // [16 rows x 128 d] as two 2 KB swizzle blocks
 constexpr int kDcLenCache = 1024;         // seq_lens cached in smem
+constexpr int kDcQBufs = 4;  // Q staging buffers: item i uses i % 4 (see the loader)
 constexpr int kDcMisc = 1024 + kDcLenCache * 4;
-constexpr int kDcSmem = kDcStages * 2 * kDcTileBytes + 4 * kDcQBytes + 1024 + kDcMisc;
+constexpr int kDcSmem = kDcStages * 2 * kDcTileBytes + (kDcQBufs + 2) * kDcQBytes + 1024 + kDcMisc;
 constexpr int kDcMaxSplits = 32;
 constexpr int kDcMaxGroup = 8;
 constexpr float kDcRescale = 8.0f;  // log2 units a score may exceed m_ref before it is raised
@@ -146,19 +153,21 @@ attn_decode_kernel(const DecodeParams p) {
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sK = smem;                                    // 3 x 32 KB
   uint8_t* sV = smem + kDcStages * kDcTileBytes;         // 3 x 32 KB
-  uint8_t* sQ = smem + 2 * kDcStages * kDcTileBytes;     // 2 x 4 KB
-  uint8_t* sP = sQ + 2 * kDcQBytes;                      // 2 x 4 KB
+  uint8_t* sQ = smem + 2 * kDcStages * kDcTileBytes;     // kDcQBufs x 4 KB
+  uint8_t* sP = sQ + kDcQBufs * kDcQBytes;               // 2 x 4 KB
   uint8_t* misc = sP + 2 * kDcQBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
-  uint64_t* kv_full = bars;        // 3
-  uint64_t* kv_empty = bars + 3;   // 3
-  uint64_t* s_full = bars + 6;     // 2
-  uint64_t* s_empty = bars + 8;    // 2
-  uint64_t* p_full = bars + 10;    // 2
-  uint64_t* p_empty = bars + 12;   // 2
-  uint64_t* o_done = bars + 14;    // 1
-  uint64_t* o_empty = bars + 15;   // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* k_full = bars;         // 3
+  uint64_t* k_empty = bars + 3;    // 3
+  uint64_t* v_full = bars + 6;     // 3
+  uint64_t* v_empty = bars + 9;    // 3
+  uint64_t* s_full = bars + 12;    // 2
+  uint64_t* s_empty = bars + 14;   // 2
+  uint64_t* p_full = bars + 16;    // 2
+  uint64_t* p_empty = bars + 18;   // 2
+  uint64_t* o_done = bars + 20;    // 1
+  uint64_t* o_empty = bars + 21;   // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
   int* flag_slot = reinterpret_cast<int*>(tmem_slot + 1);
   float* red = reinterpret_cast<float*>(misc + 256);   // [4 warps][8 heads] scratch (+ 8 totals)
   int* s_len = reinterpret_cast<int*>(misc + 1024);    // seq_lens[0 .. kDcLenCache)
@@ -171,8 +180,10 @@ attn_decode_kernel(const DecodeParams p) {
   if (warp == 8) {
     if (lane == 0) {
       for (int i = 0; i < kDcStages; ++i) {
-        mbar_init(&kv_full[i], 128);
-        mbar_init(&kv_empty[i], 1);
+        mbar_init(&k_full[i], 64);
+        mbar_init(&k_empty[i], 1);
+        mbar_init(&v_full[i], 64);
+        mbar_init(&v_empty[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
@@ -189,7 +200,7 @@ attn_decode_kernel(const DecodeParams p) {
     tmem_relinquish();
   }
   // zero P / Q staging once: rows >= G are never written and only feed ignored output columns
-  for (int i = threadIdx.x; i < (4 * kDcQBytes) / 16; i += kDcThreads)
+  for (int i = threadIdx.x; i < ((kDcQBufs + 2) * kDcQBytes) / 16; i += kDcThreads)
     reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
 
@@ -215,11 +226,12 @@ attn_decode_kernel(const DecodeParams p) {
       int ts = 0;  // global tile counter of the S stream
       auto issue_s = [&]() {
         const int st = ts % kDcStages, sb = ts & 1;
-        mbar_wait(&kv_full[st], (ts / kDcStages) & 1);
+        mbar_wait(&k_full[st], (ts / kDcStages) & 1);
+        fence_proxy_async_smem();  // cp.async (generic proxy) writes -> UMMA operand reads
         mbar_wait(&s_empty[sb], ((ts >> 1) & 1) ^ 1);
         tc_fence_after_sync();
         const uint32_t k_addr = smem_u32(sK + st * kDcTileBytes);
-        const uint32_t q_addr = smem_u32(sQ + (cs.iter & 1) * kDcQBytes);
+        const uint32_t q_addr = smem_u32(sQ + (cs.iter % kDcQBufs) * kDcQBytes);
 #pragma unroll
         for (int k = 0; k < kDcD / 16; ++k) {
           umma_ss(tmem_S + sb * kDcN,
@@ -227,6 +239,7 @@ attn_decode_kernel(const DecodeParams p) {
                   umma_desc_sw128(q_addr + (k >> 2) * 2048 + (k & 3) * 32, 16, 1024), idesc_s,
                   k > 0 ? 1u : 0u);
         }
+        umma_commit(&k_empty[st]);  // K_t: consumed once these MMAs have read it
         umma_commit(&s_full[sb]);
         ++ts;
         cs.next(p, s_len, total);
@@ -238,6 +251,8 @@ attn_decode_kernel(const DecodeParams p) {
         if (cs.valid) issue_s();
         const int st = tp % kDcStages, pb = tp & 1, ob = cp.iter & 1;
         mbar_wait(&p_full[pb], (tp >> 1) & 1);
+        mbar_wait(&v_full[st], (tp / kDcStages) & 1);
+        fence_proxy_async_smem();
         if (cp.j == 0) {
           mbar_wait(&o_empty[ob], (o_uses[ob] & 1) ^ 1);
           ++o_uses[ob];
@@ -251,7 +266,7 @@ attn_decode_kernel(const DecodeParams p) {
                   umma_desc_sw128(p_addr + (k >> 2) * 2048 + (k & 3) * 32, 16, 1024), idesc_o,
                   (cp.j > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&kv_empty[st]);
+        umma_commit(&v_empty[st]);
         umma_commit(&p_empty[pb]);
         umma_commit(o_done);
         ++tp;
@@ -259,69 +274,70 @@ attn_decode_kernel(const DecodeParams p) {
       }
     }
   } else if (warp >= 4) {
-    // ===================== K/V gather + Q staging (128 threads) =====================
-    const int lt = threadIdx.x - 128;
-    const int chunk = lt & 15;
-    const int rsub = lt >> 4;
-    const T* kp = reinterpret_cast<const T*>(p.k_pool);
-    const T* vp = reinterpret_cast<const T*>(p.v_pool);
+    // ===================== K loader (warps 4-5, + Q staging) / V loader (warps 6-7) =====================
+    // Independent rings: a K slot is free again as soon as S_t has been issued, a V slot only after
+    // PV_t (one softmax later), so the K gather runs ahead of the V gather instead of both being
+    // held back by the slower of the two.
+    const int is_v = warp >= 6 ? 1 : 0;
+    const int lt = threadIdx.x - (is_v ? 192 : 128);  // 0..63
+    const int chunk = lt & 15;   // 16-byte chunk of the 256-byte head row
+    const int rsub = lt >> 4;    // 0..3
+    const T* pool = reinterpret_cast<const T*>(is_v ? p.v_pool : p.k_pool);
+    uint8_t* ring = is_v ? sV : sK;
+    uint64_t* full = is_v ? v_full : k_full;
+    uint64_t* empty = is_v ? v_empty : k_empty;
     const int64_t row_elems = static_cast<int64_t>(p.Hk) * kDcD;
     DcCursor c;
     c.init(p, s_len, total);
     int t = 0;
-    int prev_stage = -1;
+    // Page-table lookups run ONE TILE AHEAD of the gather (32 slots per thread), so the dependent
+    // chain req_pool_indices -> req_to_token -> pool row is off the issue path.
+    auto lookup = [&](const DcCursor& cc, int* sl) {
+      const DcItem& it = cc.item;
+      const int32_t* rtt0 = p.req_to_token + p.req_pool_indices[it.b] * p.rtt_stride;
+      const int tokb = it.t0 + cc.j * kDcTile + rsub;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int tok = tokb + i * 4;
+        sl[i] = tok < it.t1 ? __ldg(rtt0 + tok) : -1;
+      }
+    };
+    int slot[32];
+    if (c.valid) lookup(c, slot);
     while (c.valid) {
       const int st = t % kDcStages;
-      const DcItem& it = c.item;
-      // Page-table lookups first, all 16 in flight at once (the cp.async asm below is a compiler
-      // barrier, so interleaving them would serialise 16 dependent global-load latencies per tile).
-      int slot[16];
-      {
-        const int32_t* rtt0 = p.req_to_token + p.req_pool_indices[it.b] * p.rtt_stride;
-        const int tokb = it.t0 + c.j * kDcTile + rsub;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int tok = tokb + i * 8;
-          slot[i] = tok < it.t1 ? __ldg(rtt0 + tok) : -1;
+      const int b = c.item.b, hk = c.item.hk, cj = c.j, citer = c.iter;
+      c.next(p, s_len, total);
+      int nslot[32];
+      if (c.valid) lookup(c, nslot);
+      mbar_wait(&empty[st], ((t / kDcStages) & 1) ^ 1);
+      if (!is_v && cj == 0) {
+        // stage the G query rows of this (request, kv head) as the K-major B operand, in the same
+        // cp.async group as the K tile.  Buffer citer % 4 was last read by the S MMAs of item
+        // citer - 4, whose tiles are all older than tile t-3 — complete once k_empty[st] fired.
+        for (int r = rsub; r < G; r += 4) {
+          const T* src = reinterpret_cast<const T*>(p.q) + b * p.q_stride +
+                         (static_cast<int64_t>(hk) * G + r) * kDcD + chunk * 8;
+          cp_async16(smem_u32(sQ + (citer % kDcQBufs) * kDcQBytes + dc_small_off(r, chunk * 8)), src, true);
         }
       }
-      mbar_wait(&kv_empty[st], ((t / kDcStages) & 1) ^ 1);
-      if (c.j == 0) {
-        // stage the G query rows of this (request, kv head) as the K-major B operand
-        if (rsub < G) {
-          const T* src = reinterpret_cast<const T*>(p.q) + it.b * p.q_stride +
-                         (static_cast<int64_t>(it.hk) * G + rsub) * kDcD + chunk * 8;
-          const uint4 v = *reinterpret_cast<const uint4*>(src);
-          *reinterpret_cast<uint4*>(sQ + (c.iter & 1) * kDcQBytes + dc_small_off(rsub, chunk * 8)) = v;
-        }
-      }
-      const int64_t col = static_cast<int64_t>(it.hk) * kDcD + chunk * 8;
-      const uint32_t kdst = smem_u32(sK + st * kDcTileBytes);
-      const uint32_t vdst = smem_u32(sV + st * kDcTileBytes);
+      const int64_t col = static_cast<int64_t>(hk) * kDcD + chunk * 8;
+      const uint32_t dst = smem_u32(ring + st * kDcTileBytes);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int row = i * 8 + rsub;
+      for (int i = 0; i < 32; ++i) {
+        const int row = i * 4 + rsub;
         const bool valid = slot[i] >= 0;
         const int64_t s64 = valid ? slot[i] : 0;
-        const uint32_t off = dc_tile_off(row, chunk);
-        cp_async16(kdst + off, kp + s64 * row_elems + col, valid);
-        cp_async16(vdst + off, vp + s64 * row_elems + col, valid);
+        cp_async16(dst + dc_tile_off(row, chunk), pool + s64 * row_elems + col, valid);
       }
-      cp_async_commit();
-      // publish the PREVIOUS tile (keeps two tiles = 128 KB in flight per SM)
-      if (prev_stage >= 0) {
-        cp_async_wait<1>();
-        fence_proxy_async_smem();
-        mbar_arrive(&kv_full[prev_stage]);
-      }
-      prev_stage = st;
+      // completion is asynchronous: the barrier receives this thread's arrival when all of its
+      // cp.asyncs above have landed — the loader never waits for data, only for a free slot, so
+      // every slot of the ring can be in flight.  (The generic->async proxy fence is on the
+      // consumer side, after its wait on this barrier.)
+      cp_async_mbar_arrive_noinc(&full[st]);
       ++t;
-      c.next(p, s_len, total);
-    }
-    if (prev_stage >= 0) {
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      mbar_arrive(&kv_full[prev_stage]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) slot[i] = nslot[i];
     }
   } else {
     // ===================== softmax / correction / epilogue =====================

@@ -121,6 +121,20 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// TMA row gather: four rows (r0..r3, arbitrary and independent) x one box width of a 2-D tensor
+// land as 4 consecutive 128-byte rows at smem_dst, swizzled by the tensor map's mode exactly as a
+// tiled load of 4 consecutive rows would be (verified on B200: scripts/probes/gather4_probe.cu).
+// The tensor map's box is {box_cols, 1}; 4 * box_cols * elemsize bytes are credited to the
+// mbarrier.  A row index outside [0, rows) is zero-filled and still credited in full.
+__device__ __forceinline__ void tma_gather4_2d(uint32_t smem_dst, const void* tmap, uint64_t* bar, int32_t col,
+                                               int32_t r0, int32_t r1, int32_t r2, int32_t r3, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(smem_dst),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "l"(policy)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // thread-block clusters: rank, cluster barrier, distributed shared memory, remote mbarrier arrive
 // ------------------------------------------------------------------------------------------------
