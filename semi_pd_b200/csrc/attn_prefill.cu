@@ -11,27 +11,33 @@
 //   * otherwise: two consecutive 128-token tiles of one query head.
 // Each query tile belongs to one softmax warpgroup (own S, P, O, running max and row sum), so a
 // K/V tile staged once in shared memory feeds 2 x 128 query rows (half the L2->SM traffic per
-// FLOP of a single-tile CTA) and the tensor core alternates between the two warpgroups: while
-// warpgroup 0 exponentiates S0_j the tensor core runs PV1_{j-1} / S1_j, and vice versa.
+// FLOP of a single-tile CTA).
+// HALF-TILE UNITS.  A 128-token K/V tile is consumed as two independent 64-column halves a / b of
+// the warpgroup's S tile (S_a = Q K[0:64]^T in TMEM columns 0-63, S_b in 64-127, each with its own
+// full / P-ready barriers).  While a warpgroup exponentiates half b of tile j, the tensor core
+// runs PV_a(j) and S_a(j+1) for it, so its softmax never waits for the S -> softmax -> PV -> S
+// chain of the whole tile (ncu on the whole-tile version: softmax warps 50 % of their time on
+// s_full, tensor pipe 44 %); the second warpgroup fills the remaining tensor time.
 // Roles (384 threads):
 //   warps 0-3 / 4-7  softmax warpgroup 0 / 1: one thread per query row, ONE pass per tile in the
 //                    exp2 domain against a lazily raised reference max (O in TMEM is rescaled only
 //                    when a row outgrows it by 2^8 — then the tile is redone; rare after tile 0).
 //                    P never touches shared memory: the 16-bit probabilities are written back
-//                    into TMEM over the first 64 columns of the S tile they came from
+//                    into TMEM over the first 32 columns of the S half they came from
 //                    (tcgen05.st) and feed the PV MMA as its A operand from TMEM;
 //                    epilogue O / l straight from TMEM to global memory;
 //   warp 8, warp 9   K / V loader: gather rows through req_to_token with 16-byte cp.async into
 //                    128-byte-swizzled smem; one 5-slot ring K_j V_j K_{j+1} ... runs ahead of the
 //                    consumer ACROSS items, so an item's first tiles are in flight while the
 //                    previous item drains;
-//   warp 10          MMA issuer: S_w = Q_w K_j^T (both K-major in smem), O_w += P_w V_j (P from
-//                    TMEM, V MN-major in smem); per warpgroup the order is PV_j then S_{j+1}
-//                    (S_{j+1} overwrites the columns P_j lives in; tcgen05.mma executes in order);
+//   warp 10          MMA issuer: S_w,h = Q_w K_j[h]^T (both K-major in smem), O_w += P_w,h V_j[h] (P
+//                    from TMEM, V MN-major in smem); per warpgroup and half the order is PV(j,h)
+//                    then S(j+1,h) (which overwrites the columns P(j,h) lives in; tcgen05.mma
+//                    executes in order);
 //   warp 11          Q loader (TMA): the next item's Q tiles are fetched as soon as the current
 //                    item's last S MMA has read them.
 // Items are ordered heaviest (latest query tiles) first and dealt to the CTAs in snake order.
-// smem: Q0 Q1 + 5 K/V slots = 7 x 32 KB.  TMEM: S0/P0 | S1/P1 | O0 | O1 = 512 columns.
+// smem: Q0 Q1 + 5 K/V slots = 7 x 32 KB.  TMEM: S0a/P0a S0b/P0b | S1a/P1a S1b/P1b | O0 | O1 = 512 columns.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -43,6 +49,7 @@ namespace spd {
 constexpr int kPfThreads = 384;  // 12 warps -> 168 registers per thread for the softmax warps
 constexpr int kPfM = 128;    // query rows per warpgroup tile
 constexpr int kPfN = 128;    // kv tokens per tile
+constexpr int kPfH = 64;     // kv tokens per half-tile unit (columns of one S half)
 constexpr int kPfD = 128;    // head dim
 constexpr int kTileBytes = 128 * 128 * 2;  // one [128 x 128] 16-bit tile = two 16 KB swizzle blocks
 constexpr int kPfSlots = 5;
@@ -131,50 +138,69 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       : "memory");
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2): one instruction per two elements.  The softmax warps
+// are issue-bound around the MUFU stream (one warp per scheduler and warpgroup), so halving the
+// FFMA / FADD count is what shortens a row pass.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // 32 columns of one tile row: p = exp2(s*scale - m_off), packed to 16 bits into pk[0..16)
 template <typename T, bool kMask>
-__device__ __forceinline__ void softmax_chunk(const uint32_t* r, int c, uint32_t* pk, float scale_log2,
-                                              float m_off, int kv0, int limit, float& ps0, float& ps1) {
+__device__ __forceinline__ void softmax_chunk(const uint32_t* r, int c, uint32_t* pk, uint64_t scale2,
+                                              uint64_t neg_m2, int kv0, int limit, uint64_t& ps) {
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
-    float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -m_off));
-    float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_off));
+    float x0, x1;
+    unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), scale2, neg_m2), x0, x1);
+    float p0 = fast_exp2(x0);
+    float p1 = fast_exp2(x1);
     if constexpr (kMask) {
       p0 = (kv0 + c + i) <= limit ? p0 : 0.f;
       p1 = (kv0 + c + i + 1) <= limit ? p1 : 0.f;
     }
-    ps0 += p0;
-    ps1 += p1;
+    ps = fadd2(ps, pack_f32x2(p0, p1));
     pk[i >> 1] = pack2<T>(p0, p1);
   }
 }
 
-// One tile row for one thread: S (TMEM) -> 64 packed 16-bit pairs in registers.  Returns the row
-// sum of p (masked entries excluded).  The TMEM loads are software-pipelined (the next 32 columns
-// are in flight while the current 32 are exponentiated): with one softmax warp per scheduler
-// nothing else hides the tcgen05.ld latency.  kMask is a template parameter so that the unmasked
-// tiles run the lean loop: FFMA + MUFU.EX2 + FADD + half an F2FP per element.
+// One row of one S half for one thread: 64 columns of S (TMEM) -> 32 packed 16-bit pairs in
+// registers.  Returns the row sum of p (masked entries excluded).  The second TMEM load is in
+// flight while the first 32 columns are exponentiated.  kMask is a template parameter so that the
+// unmasked units run the lean loop: FFMA + MUFU.EX2 + FADD + half an F2FP per element.
 template <typename T, bool kMask>
 __device__ __forceinline__ float softmax_row_pass(uint32_t ts, uint32_t* pk, float scale_log2, float m_off,
                                                   int kv0, int limit) {
-  float ps0 = 0.f, ps1 = 0.f;
+  const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
+  const uint64_t neg_m2 = pack_f32x2(-m_off, -m_off);
+  uint64_t ps = pack_f32x2(0.f, 0.f);
   uint32_t ra[32], rb[32];
   tmem_ld_32x32b_x32(ts, ra);
-  tmem_ld_wait();
   tmem_ld_32x32b_x32(ts + 32, rb);
-  softmax_chunk<T, kMask>(ra, 0, pk, scale_log2, m_off, kv0, limit, ps0, ps1);
   tmem_ld_wait();
-  tmem_ld_32x32b_x32(ts + 64, ra);
-  softmax_chunk<T, kMask>(rb, 32, pk + 16, scale_log2, m_off, kv0, limit, ps0, ps1);
-  tmem_ld_wait();
-  tmem_ld_32x32b_x32(ts + 96, rb);
-  softmax_chunk<T, kMask>(ra, 64, pk + 32, scale_log2, m_off, kv0, limit, ps0, ps1);
-  tmem_ld_wait();
-  softmax_chunk<T, kMask>(rb, 96, pk + 48, scale_log2, m_off, kv0, limit, ps0, ps1);
+  softmax_chunk<T, kMask>(ra, 0, pk, scale2, neg_m2, kv0, limit, ps);
+  softmax_chunk<T, kMask>(rb, 32, pk + 16, scale2, neg_m2, kv0, limit, ps);
+  float ps0, ps1;
+  unpack_f32x2(ps, ps0, ps1);
   return ps0 + ps1;
 }
 
-// max of the visible raw scores of one row of S (TMEM)
+// max of the visible raw scores of one row of an S half (TMEM)
 template <bool kMask>
 __device__ __forceinline__ void rowmax_chunk(const uint32_t* r, int c, int kv0, int limit, float& m0, float& m1) {
 #pragma unroll
@@ -196,12 +222,7 @@ __device__ __forceinline__ float softmax_row_max(uint32_t ts, int kv0, int limit
   tmem_ld_32x32b_x32(ts + 32, rb);
   tmem_ld_wait();
   rowmax_chunk<kMask>(ra, 0, kv0, limit, m0, m1);
-  tmem_ld_32x32b_x32(ts + 64, ra);
   rowmax_chunk<kMask>(rb, 32, kv0, limit, m0, m1);
-  tmem_ld_32x32b_x32(ts + 96, rb);
-  tmem_ld_wait();
-  rowmax_chunk<kMask>(ra, 64, kv0, limit, m0, m1);
-  rowmax_chunk<kMask>(rb, 96, kv0, limit, m0, m1);
   return fmaxf(m0, m1);
 }
 
@@ -218,10 +239,10 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
   uint64_t* q_empty = bars + 1;                // 1
   uint64_t* kv_full = bars + 2;                // kPfSlots
   uint64_t* kv_empty = kv_full + kPfSlots;     // kPfSlots
-  uint64_t* s_full = kv_empty + kPfSlots;      // 2 (per warpgroup)
-  uint64_t* p_full = s_full + 2;               // 2
-  uint64_t* pv_done = p_full + 2;              // 2
-  uint64_t* o_free = pv_done + 2;              // 2
+  uint64_t* s_full = kv_empty + kPfSlots;      // 4: [warpgroup][half]
+  uint64_t* p_full = s_full + 4;               // 4: [warpgroup][half]
+  uint64_t* pv_done = p_full + 4;              // 4: [warpgroup][half] (see the parity note in the softmax)
+  uint64_t* o_free = pv_done + 4;              // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -236,12 +257,12 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
         mbar_init(&kv_full[i], 32);
         mbar_init(&kv_empty[i], 1);
       }
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < 4; ++i) {
         mbar_init(&s_full[i], 1);
         mbar_init(&p_full[i], 4);
         mbar_init(&pv_done[i], 1);
-        mbar_init(&o_free[i], 4);
       }
+      for (int i = 0; i < 2; ++i) mbar_init(&o_free[i], 4);
       fence_barrier_init();
     }
     __syncwarp();
@@ -253,7 +274,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns (warpgroup 0 / 1); P aliases cols 0..63
+  const uint32_t tmem_S = tmem_base;        // 2 x (64 + 64) columns (warpgroup 0 / 1, half a / b); P_h aliases
+                                            // the first 32 columns of S_h
   const uint32_t tmem_O = tmem_base + 256;  // 2 x 128 columns
 
   griddep_wait();
@@ -282,10 +304,10 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
   } else if (warp == 10) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      constexpr uint32_t idesc_qk = umma_idesc<T>(kPfM, kPfN, 0, 0);  // A, B K-major
+      constexpr uint32_t idesc_qk = umma_idesc<T>(kPfM, kPfH, 0, 0);  // A, B K-major; N = one half
       constexpr uint32_t idesc_pv = umma_idesc<T>(kPfM, kPfD, 0, 1);  // A = P (TMEM), B = V MN-major
       uint32_t t_base = 0;          // tiles of all previous items (ring position / 2)
-      uint32_t pq[2] = {0, 0};      // PV tiles issued per warpgroup (all items)
+      uint32_t pq[2] = {0, 0};      // PV units issued per warpgroup (all items); half = pq & 1
       uint32_t eq[2] = {0, 0};      // items per warpgroup (o_free phase)
       uint32_t itn = 0;
       for (int kk = 0;; ++kk) {
@@ -294,58 +316,62 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
         const PfItem it = pf_item(p, idx);
         if (it.n == 0) continue;
         mbar_wait(q_full, itn & 1);
-        // S_w(j): the warpgroup's previous P (aliasing S) has been consumed by PV_{j-1}, issued
-        // earlier by this thread — tcgen05.mma executes in issue order
-        auto issue_s = [&](int w, int j) {
+        // S_w(j, h): the warpgroup's previous P in these columns has been consumed by PV(j-1, h),
+        // issued earlier by this thread — tcgen05.mma executes in issue order
+        auto issue_s = [&](int w, int j, int h) {
           const uint32_t pos = 2 * (t_base + j);
           mbar_wait(&kv_full[pos % kPfSlots], (pos / kPfSlots) & 1);
           tc_fence_after_sync();
           const uint32_t q_addr = smem_u32(sQ + w * kTileBytes);
-          const uint32_t k_addr = smem_u32(sKV + (pos % kPfSlots) * kTileBytes);
+          const uint32_t k_addr = smem_u32(sKV + (pos % kPfSlots) * kTileBytes) + h * (kPfH * 128);
 #pragma unroll
           for (int k = 0; k < kPfD / 16; ++k) {
             const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-            umma_ss(tmem_S + w * kPfN, umma_desc_sw128(q_addr + off, 16, 1024),
+            umma_ss(tmem_S + w * kPfN + h * kPfH, umma_desc_sw128(q_addr + off, 16, 1024),
                     umma_desc_sw128(k_addr + off, 16, 1024), idesc_qk, k > 0 ? 1u : 0u);
           }
-          umma_commit(&s_full[w]);
+          umma_commit(&s_full[w * 2 + h]);
         };
-        // after the S MMAs of tile j (both warpgroups) have been issued: release K_j, and Q after
+        // after both halves of S(j) of both warpgroups have been issued: release K_j, and Q after
         // the item's last S
         auto s_tile_issued = [&](int j) {
           umma_commit(&kv_empty[(2 * (t_base + j)) % kPfSlots]);
           if (j == it.n - 1) umma_commit(q_empty);
         };
+        // the epilogue of the previous item reads O, not S — and its last PVs (reading P in the S
+        // columns) were issued before these, so S(0, a/b) may go out immediately
 #pragma unroll
-        for (int w = 0; w < 2; ++w)
-          if (it.nt[w] > 0) {
-            // the epilogue of the previous item reads O, not S — but its last PV (reading P in the
-            // S columns) was issued before this S, so S_0 may go out immediately
-            issue_s(w, 0);
-          }
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int w = 0; w < 2; ++w)
+            if (it.nt[w] > 0) issue_s(w, 0, h);
         s_tile_issued(0);
         for (int j = 0; j < it.n; ++j) {
           const uint32_t vpos = 2 * (t_base + j) + 1;
 #pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            if (j >= it.nt[w]) continue;
-            mbar_wait(&p_full[w], pq[w] & 1);
-            mbar_wait(&kv_full[vpos % kPfSlots], (vpos / kPfSlots) & 1);
-            if (j == 0) mbar_wait(&o_free[w], (eq[w] & 1) ^ 1);  // previous item's O has been read
-            tc_fence_after_sync();
-            const uint32_t v_addr = smem_u32(sKV + (vpos % kPfSlots) * kTileBytes);
+          for (int h = 0; h < 2; ++h) {
 #pragma unroll
-            for (int k = 0; k < kPfN / 16; ++k) {
-              // A = P[128 x 16 kv]: 8 TMEM columns per k-step; B = V[16 kv x 128 d] (MN-major: 2
-              // blocks of 64 d, LBO = 16 KB; kv rows 128 B apart, 8-row groups SBO = 1 KB)
-              umma_ts(tmem_O + w * kPfD, tmem_S + w * kPfN + k * 8,
-                      umma_desc_sw128(v_addr + k * 2048, 16384, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+            for (int w = 0; w < 2; ++w) {
+              if (j >= it.nt[w]) continue;
+              mbar_wait(&p_full[w * 2 + h], (pq[w] >> 1) & 1);
+              mbar_wait(&kv_full[vpos % kPfSlots], (vpos / kPfSlots) & 1);
+              if (j == 0 && h == 0) mbar_wait(&o_free[w], (eq[w] & 1) ^ 1);  // previous item's O has been read
+              tc_fence_after_sync();
+              const uint32_t v_addr = smem_u32(sKV + (vpos % kPfSlots) * kTileBytes) + h * (kPfH * 128);
+#pragma unroll
+              for (int k = 0; k < kPfH / 16; ++k) {
+                // A = P[128 x 16 kv]: 8 TMEM columns per k-step; B = V[16 kv x 128 d] (MN-major: 2
+                // blocks of 64 d, LBO = 16 KB; kv rows 128 B apart, 8-row groups SBO = 1 KB)
+                umma_ts(tmem_O + w * kPfD, tmem_S + w * kPfN + h * kPfH + k * 8,
+                        umma_desc_sw128(v_addr + k * 2048, 16384, 1024), idesc_pv,
+                        (j > 0 || h > 0 || k > 0) ? 1u : 0u);
+              }
+              umma_commit(&pv_done[w * 2 + h]);
+              ++pq[w];
+              if (j + 1 < it.nt[w]) issue_s(w, j + 1, h);
             }
-            umma_commit(&pv_done[w]);
-            ++pq[w];
-            if (j + 1 < it.nt[w]) issue_s(w, j + 1);
           }
-          umma_commit(&kv_empty[vpos % kPfSlots]);  // V_j: both PVs issued
+          umma_commit(&kv_empty[vpos % kPfSlots]);  // V_j: all PVs issued
           if (j + 1 < it.n) s_tile_issued(j + 1);
         }
 #pragma unroll
@@ -424,7 +450,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t ts = tmem_S + lane_base + w * kPfN;
     const uint32_t to = tmem_O + lane_base + w * kPfD;
-    uint32_t u = 0;  // tiles processed by this warpgroup (all items)
+    uint32_t u = 0;  // half-tile units processed by this warpgroup (all items); half = u & 1
     for (int k = 0;; ++k) {
       const int idx = pf_rank(k, cta, ncta);
       if (idx >= p.total_items) break;
@@ -438,31 +464,39 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
       const int limit = it.pre + m0 + row;  // last visible key of this row (causal)
       float m_used = -INFINITY;  // max currently folded into O and l (raw score units)
       float l = 0.f;
-      for (int j = 0; j < nt; ++j, ++u) {
-        const int kv0 = j * kPfN;
-        const bool need_mask = (kv0 + kPfN - 1) > (it.pre + m0);
-        mbar_wait(&s_full[w], u & 1);
+      for (int jh = 0; jh < 2 * nt; ++jh, ++u) {
+        const int h = jh & 1;
+        const int kv0 = (jh >> 1) * kPfN + h * kPfH;
+        const bool need_mask = (kv0 + kPfH - 1) > (it.pre + m0);
+        const uint32_t tsh = ts + h * kPfH;
+        mbar_wait(&s_full[w * 2 + h], (u >> 1) & 1);
         tc_fence_after_sync();
-        if (j == 0) {
-          // first tile of the item: establish the reference max with a max-only pre-pass
-          m_used = need_mask ? softmax_row_max<true>(ts, kv0, limit) : softmax_row_max<false>(ts, kv0, limit);
+        if (jh == 0) {
+          // first unit of the item: establish the reference max with a max-only pre-pass
+          m_used = need_mask ? softmax_row_max<true>(tsh, kv0, limit) : softmax_row_max<false>(tsh, kv0, limit);
         }
         float m_off = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
-        uint32_t pk[64];
-        float psum = need_mask ? softmax_row_pass<T, true>(ts, pk, p.scale_log2, m_off, kv0, limit)
-                               : softmax_row_pass<T, false>(ts, pk, p.scale_log2, m_off, kv0, limit);
+        uint32_t pk[32];
+        float psum = need_mask ? softmax_row_pass<T, true>(tsh, pk, p.scale_log2, m_off, kv0, limit)
+                               : softmax_row_pass<T, false>(tsh, pk, p.scale_log2, m_off, kv0, limit);
         // raise the reference max only when some row may have outgrown it by > 2^8 (an element
         // above 2^8 implies a row sum above 2^8; warp-uniform decision: tcgen05.ld/st are
-        // warp-collective); S is still intact (P is stored below), so the tile is simply redone
+        // warp-collective); S is still intact (P is stored below), so the unit is simply redone
         if (__any_sync(0xffffffffu, psum > kRescaleTrigger)) {
-          const float mx = need_mask ? softmax_row_max<true>(ts, kv0, limit) : softmax_row_max<false>(ts, kv0, limit);
+          const float mx = need_mask ? softmax_row_max<true>(tsh, kv0, limit) : softmax_row_max<false>(tsh, kv0, limit);
           const float m_new = fmaxf(m_used, mx);
           const float alpha = (m_used == -INFINITY) ? 0.f : fast_exp2((m_used - m_new) * p.scale_log2);
           l *= alpha;
           m_used = m_new;
           m_off = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
-          if (j > 0) {
-            // S_j was issued after PV_{j-1}: O is complete up to tile j-1
+          if (jh > 0) {
+            // O must be quiescent: S of this unit was issued after PV of unit u-2 (so units <= u-2
+            // are complete), but PV of unit u-1 (the other half) may still be running.  pv_done
+            // is per half so that this wait cannot alias: on the other half's barrier at most
+            // the one phase we wait for is outstanding (a parity wait only tells the current
+            // phase from the one before it).
+            mbar_wait(&pv_done[w * 2 + ((u - 1) & 1)], ((u - 1) >> 1) & 1);
+            tc_fence_after_sync();
 #pragma unroll 1
             for (int c = 0; c < kPfD; c += 32) {
               uint32_t r[32];
@@ -473,20 +507,21 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
               tmem_st_32x32b_x32(to + c, r);
             }
           }
-          psum = need_mask ? softmax_row_pass<T, true>(ts, pk, p.scale_log2, m_off, kv0, limit)
-                           : softmax_row_pass<T, false>(ts, pk, p.scale_log2, m_off, kv0, limit);
+          psum = need_mask ? softmax_row_pass<T, true>(tsh, pk, p.scale_log2, m_off, kv0, limit)
+                           : softmax_row_pass<T, false>(tsh, pk, p.scale_log2, m_off, kv0, limit);
         }
         l += psum;
-        // P_j over the first 64 columns of S_j (every column of S_j is in registers by now)
-        tmem_st_32x32b_x32(ts, pk);
-        tmem_st_32x32b_x32(ts + 32, pk + 32);
+        // P over the first 32 columns of this S half (every column of it is in registers by now)
+        tmem_st_32x32b_x32(tsh, pk);
         tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[w]);
+        if (lane == 0) mbar_arrive(&p_full[w * 2 + h]);
       }
       // ---- epilogue: O / l, TMEM -> registers -> global ----
-      mbar_wait(&pv_done[w], (u - 1) & 1);
+      // last unit = half b of the last tile; S of that unit complete => PV(b) of the tile before is
+      // complete, so only this one phase of pv_done[w][b] can be outstanding; PV(b) complete => PV(a)
+      mbar_wait(&pv_done[w * 2 + 1], ((u >> 1) - 1) & 1);
       tc_fence_after_sync();
       const float inv_l = l > 0.f ? 1.f / l : 0.f;
       T* dst = reinterpret_cast<T*>(p.out) + static_cast<int64_t>(q_row0 + row) * p.out_stride +
