@@ -10,9 +10,15 @@
 //     i.e. the weight dimension feeds UMMA-M (128 TMEM lanes) and the few tokens feed UMMA-N,
 //     so streaming the weights at HBM speed is the only cost.  Work is scheduled STREAM-K style:
 //     the (tile x k-block) unit space is cut into one equal contiguous range per CTA, so every SM
-//     streams the same number of weight bytes whatever N is (32 tiles or 1002); a tile that is
-//     shared by several CTAs is summed from fp32 partials by its last-arriving CTA in a fixed
-//     order (bit-deterministic, no atomics on data).
+//     streams the same number of weight bytes whatever N is (32 tiles or 1002) and whatever SM
+//     budget the caller's partition has.  A tile shared by several CTAs is finished by its OWNER,
+//     the CTA holding the tile's last k-blocks: that segment is always the owner's first, so its
+//     accumulator stays parked in TMEM while the CTA works through the rest of its range; the
+//     other contributors dump fp32 partials (coalesced, L2-resident) as their last piece of work
+//     and raise a flag; at the very end the owner adds the partials in ascending-k order to its
+//     parked accumulator and stores C.  Nobody waits before having published its own partial
+//     (no deadlock, all CTAs are co-resident), the wait is short because every CTA has the same
+//     amount of work, and the sum order is fixed (bit-deterministic, no atomics on data).
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
 // warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global).
@@ -45,8 +51,8 @@ struct GemmParams {
   int streamk;       // 0: whole tiles, strided over CTAs; 1: equal unit ranges (decode regime)
   int panel;         // tile rasterisation: y tiles per panel (see tile_coords)
   int out_f32;
-  float* ws;        // stream-K partials: [cta][2][lane][col]
-  int* counters;    // one per tile
+  float* ws;        // stream-K partials: one [col/4][lane][4] fp32 tile per CTA
+  int* counters;    // stream-K: one 'partial published' flag per CTA
 };
 
 template <int BN>
@@ -134,7 +140,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   constexpr int kStages = gemm_stages<BN>();
   constexpr int kXBytes = kBM * kBK * 2;
   constexpr int kYBytes = BN * kBK * 2;
-  constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
+  constexpr int kTmemCols = (2 * BN) <= 32 ? 32 : (2 * BN) <= 64 ? 64 : (2 * BN) <= 128 ? 128 : (2 * BN) <= 256 ? 256 : 512;
   constexpr int kBNOut = (kEpi == SPD_EPI_SILU_MUL) ? BN / 2 : BN;  // output columns per tile
   constexpr int kChunk = BN >= 32 ? 32 : 16;
   static_assert(!(kSwap && kEpi == SPD_EPI_SILU_MUL), "fused SiLU*mul only in the non-swapped regime");
@@ -150,7 +156,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   uint64_t* tfull = bars + 2 * kStages;      // [2]
   uint64_t* tempty = bars + 2 * kStages + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  int* flag_slot = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -217,9 +222,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       it.init(p);
       int tile, kb0, kb1, slot;
       while (it.next(tile, kb0, kb1, slot)) {
-        const int as = n & 1, aphase = (n >> 1) & 1;
+        // stream-K: slot 0 is reserved for the first segment (parked until the end if this CTA
+        // owns that tile), every later segment goes through slot 1
+        const int as = p.streamk ? (n == 0 ? 0 : 1) : (n & 1);
+        const int use = p.streamk ? (n == 0 ? 0 : n - 1) : (n >> 1);
         ++n;
-        mbar_wait(&tempty[as], aphase ^ 1);
+        mbar_wait(&tempty[as], (use & 1) ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -244,147 +252,196 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
     const int row = q * 32 + lane;     // D row == TMEM lane
     const int et = threadIdx.x - 128;  // 0..127 among the epilogue threads
     const long long units = static_cast<long long>(p.x_tiles) * p.y_tiles * p.kblocks;
+    // columns that carry data (swap-AB: tokens), rounded up to the 32-column chunk
+    const int n_cols = kSwap ? static_cast<int>(((p.y_rows + kChunk - 1) / kChunk) * kChunk) : BN;
+    const int cols_used = n_cols < BN ? n_cols : BN;
+
+    // v[0..kChunk) of output chunk c of tile (xt, yt) -> C
+    auto store_chunk = [&](int xt, int yt, int c, const float* v) {
+      if constexpr (!kSwap) {
+        const int64_t m = static_cast<int64_t>(xt) * kBM + row;
+        const int64_t n0 = static_cast<int64_t>(yt) * kBNOut + c;
+        if (m < p.x_rows) {
+          if (p.out_f32) {
+            float* dst = reinterpret_cast<float*>(p.C) + m * p.ldc + n0;
+#pragma unroll
+            for (int j = 0; j < kChunk; j += 4) {
+              if (n0 + j < p.y_rows) {
+                float4 o;
+                o.x = to_f32<T>(from_f32<T>(v[j]));
+                o.y = to_f32<T>(from_f32<T>(v[j + 1]));
+                o.z = to_f32<T>(from_f32<T>(v[j + 2]));
+                o.w = to_f32<T>(from_f32<T>(v[j + 3]));
+                *reinterpret_cast<float4*>(dst + j) = o;
+              }
+            }
+          } else {
+            T* dst = reinterpret_cast<T*>(p.C) + m * p.ldc + n0;
+#pragma unroll
+            for (int j = 0; j < kChunk; j += 8) {
+              if (n0 + j < p.y_rows) {
+                uint4 o;
+                o.x = pack2<T>(v[j], v[j + 1]);
+                o.y = pack2<T>(v[j + 2], v[j + 3]);
+                o.z = pack2<T>(v[j + 4], v[j + 5]);
+                o.w = pack2<T>(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(dst + j) = o;
+              }
+            }
+          }
+        }
+      } else {
+        // swapped: lane index runs along N (contiguous in C), column j is the token
+        const int64_t nn = static_cast<int64_t>(xt) * kBM + row;
+        if (nn < p.x_rows) {
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j) {
+            const int64_t m = static_cast<int64_t>(yt) * BN + c + j;
+            if (m < p.y_rows) {
+              if (p.out_f32)
+                reinterpret_cast<float*>(p.C)[m * p.ldc + nn] = to_f32<T>(from_f32<T>(v[j]));
+              else
+                reinterpret_cast<T*>(p.C)[m * p.ldc + nn] = from_f32<T>(v[j]);
+            }
+          }
+        }
+      }
+    };
+
     int n = 0;
+    int own_tile = -1;  // stream-K: tile whose accumulator is parked in TMEM slot 0
     SegIter it;
     it.init(p);
     int tile, kb0, kb1, slot;
     while (it.next(tile, kb0, kb1, slot)) {
       int xt, yt;
       tile_coords(p, tile, xt, yt);
-      const int as = n & 1, aphase = (n >> 1) & 1;
+      const int as = p.streamk ? (n == 0 ? 0 : 1) : (n & 1);
+      const int use = p.streamk ? (n == 0 ? 0 : n - 1) : (n >> 1);
       ++n;
-      mbar_wait(&tfull[as], aphase);
+      const bool complete = (kb0 == 0 && kb1 == p.kblocks);
+      if (!complete && kb1 == p.kblocks) {
+        // this CTA holds the tile's last k-blocks: it owns the tile.  Always the CTA's first
+        // segment -> TMEM slot 0, which stays parked until the fix-up after the loop.
+        own_tile = tile;
+        continue;
+      }
+      mbar_wait(&tfull[as], use & 1);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      const bool complete = (kb0 == 0 && kb1 == p.kblocks);
-      bool do_store = true;
-      int c_first = 0, c_last = 0;
 
       if (!complete) {
-        // dump this CTA's fp32 partial ([lane][col], each thread owns one contiguous row), then
-        // the last-arriving contributor of the tile sums all of them
-        float* mine = p.ws + (static_cast<size_t>(blockIdx.x) * 2 + slot) * (kBM * BN) + row * BN;
+        // contributor (always this CTA's last segment): publish the fp32 partial.  Layout
+        // [col/4][lane][4]: one warp store covers 512 contiguous bytes.
+        float* mine = p.ws + static_cast<size_t>(blockIdx.x) * (kBM * BN) + row * 4;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += kChunk) {
+        for (int c = 0; c < cols_used; c += kChunk) {
           uint32_t r[kChunk];
           if constexpr (kChunk == 32) tmem_ld_32x32b_x32(taddr + c, r);
           else tmem_ld_32x32b_x16(taddr + c, r);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < kChunk; j += 4)
-            *reinterpret_cast<uint4*>(mine + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            *reinterpret_cast<uint4*>(mine + static_cast<size_t>((c + j) >> 2) * (kBM * 4)) =
+                make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
         }
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[as]);
-        // contributors of this tile = the CTAs whose unit ranges intersect it
-        const long long t0 = static_cast<long long>(tile) * p.kblocks;
-        c_first = static_cast<int>(((t0 + 1) * gridDim.x - 1) / units);
-        c_last = static_cast<int>(((t0 + p.kblocks) * gridDim.x - 1) / units);
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0) *flag_slot = atomicAdd(&p.counters[tile], 1);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        do_store = (*flag_slot == c_last - c_first);
-        if (do_store) __threadfence();
+        if (et == 0) {
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.counters + blockIdx.x), "r"(1) : "memory");
+        }
+        continue;
       }
 
-      if (do_store) {
 #pragma unroll 1
-        for (int c = 0; c < kBNOut; c += kChunk) {
-          float v[kChunk];
-          if (!complete) {
+      for (int c = 0; c < (kSwap ? cols_used : kBNOut); c += kChunk) {
+        float v[kChunk];
+        uint32_t r[kChunk];
+        if constexpr (kChunk == 32) tmem_ld_32x32b_x32(taddr + c, r);
+        else tmem_ld_32x32b_x16(taddr + c, r);
+        if constexpr (kEpi == SPD_EPI_SILU_MUL) {
+          uint32_t u[kChunk];
+          tmem_ld_32x32b_x32(taddr + kBNOut + c, u);
+          tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < kChunk; ++j) v[j] = 0.f;
-            // fixed summation order (ascending CTA = ascending k) -> deterministic
-            for (int cc = c_first; cc <= c_last; ++cc) {
-              // a contributor's piece of this tile is its FIRST segment iff its range starts in it
-              const long long st = SegIter::range_start(cc, units, gridDim.x);
-              const int sl = (st / p.kblocks == tile) ? 0 : 1;
-              const float* ps = p.ws + (static_cast<size_t>(cc) * 2 + sl) * (kBM * BN) + row * BN + c;
+          for (int j = 0; j < kChunk; ++j) {
+            // gate_up_proj output is rounded to T before SiluAndMul reads it
+            const float g = to_f32<T>(from_f32<T>(__uint_as_float(r[j])));
+            const float up = to_f32<T>(from_f32<T>(__uint_as_float(u[j])));
+            v[j] = g / (1.0f + __expf(-g)) * up;
+          }
+        } else {
+          tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < kChunk; j += 4) {
-                const float4 f = __ldcg(reinterpret_cast<const float4*>(ps + j));
-                v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
-              }
-            }
-          } else {
-            uint32_t r[kChunk];
-            if constexpr (kChunk == 32) tmem_ld_32x32b_x32(taddr + c, r);
-            else tmem_ld_32x32b_x16(taddr + c, r);
-            if constexpr (kEpi == SPD_EPI_SILU_MUL) {
-              uint32_t u[kChunk];
-              tmem_ld_32x32b_x32(taddr + kBNOut + c, u);
-              tmem_ld_wait();
+          for (int j = 0; j < kChunk; ++j) v[j] = __uint_as_float(r[j]);
+        }
+        store_chunk(xt, yt, c, v);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+
+    if (own_tile >= 0) {
+      // ---- deferred fix-up of the owned tile: partials of the other contributors (ascending CTA
+      // = ascending k) + the parked accumulator, in that fixed order ----
+      int xt, yt;
+      tile_coords(p, own_tile, xt, yt);
+      const long long t0 = static_cast<long long>(own_tile) * p.kblocks;
+      const int c_first = static_cast<int>(((t0 + 1) * gridDim.x - 1) / units);
+      const int c_last = static_cast<int>(blockIdx.x);  // == ((t0 + kblocks) * grid - 1) / units
+      mbar_wait(&tfull[0], 0);
+      tc_fence_after_sync();
+      for (int cc = c_first + et; cc < c_last; cc += 128) {
+        int f;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(p.counters + cc) : "memory");
+        } while (f == 0);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < cols_used; c += kChunk) {
+        float v[kChunk];
 #pragma unroll
-              for (int j = 0; j < kChunk; ++j) {
-                // gate_up_proj output is rounded to T before SiluAndMul reads it
-                const float g = to_f32<T>(from_f32<T>(__uint_as_float(r[j])));
-                const float up = to_f32<T>(from_f32<T>(__uint_as_float(u[j])));
-                v[j] = g / (1.0f + __expf(-g)) * up;
-              }
-            } else {
-              tmem_ld_wait();
+        for (int j = 0; j < kChunk; ++j) v[j] = 0.f;
+        // the partials of up to 4 contributors are requested together (independent L2 round
+        // trips), then added in ascending-k order
+        for (int cc0 = c_first; cc0 < c_last; cc0 += 4) {
+          float4 f[4][kChunk / 4];
 #pragma unroll
-              for (int j = 0; j < kChunk; ++j) v[j] = __uint_as_float(r[j]);
+          for (int i = 0; i < 4; ++i) {
+            if (cc0 + i < c_last) {
+              const float* ps = p.ws + static_cast<size_t>(cc0 + i) * (kBM * BN) + row * 4;
+#pragma unroll
+              for (int j = 0; j < kChunk; j += 4)
+                f[i][j >> 2] = __ldcg(reinterpret_cast<const float4*>(ps + static_cast<size_t>((c + j) >> 2) * (kBM * 4)));
             }
           }
-          if constexpr (!kSwap) {
-            const int64_t m = static_cast<int64_t>(xt) * kBM + row;
-            const int64_t n0 = static_cast<int64_t>(yt) * kBNOut + c;
-            if (m < p.x_rows) {
-              if (p.out_f32) {
-                float* dst = reinterpret_cast<float*>(p.C) + m * p.ldc + n0;
 #pragma unroll
-                for (int j = 0; j < kChunk; j += 4) {
-                  if (n0 + j < p.y_rows) {
-                    float4 o;
-                    o.x = to_f32<T>(from_f32<T>(v[j]));
-                    o.y = to_f32<T>(from_f32<T>(v[j + 1]));
-                    o.z = to_f32<T>(from_f32<T>(v[j + 2]));
-                    o.w = to_f32<T>(from_f32<T>(v[j + 3]));
-                    *reinterpret_cast<float4*>(dst + j) = o;
-                  }
-                }
-              } else {
-                T* dst = reinterpret_cast<T*>(p.C) + m * p.ldc + n0;
+          for (int i = 0; i < 4; ++i) {
+            if (cc0 + i < c_last) {
 #pragma unroll
-                for (int j = 0; j < kChunk; j += 8) {
-                  if (n0 + j < p.y_rows) {
-                    uint4 o;
-                    o.x = pack2<T>(v[j], v[j + 1]);
-                    o.y = pack2<T>(v[j + 2], v[j + 3]);
-                    o.z = pack2<T>(v[j + 4], v[j + 5]);
-                    o.w = pack2<T>(v[j + 6], v[j + 7]);
-                    *reinterpret_cast<uint4*>(dst + j) = o;
-                  }
-                }
-              }
-            }
-          } else {
-            // swapped: lane index runs along N (contiguous in C), column j is the token
-            const int64_t nn = static_cast<int64_t>(xt) * kBM + row;
-            if (nn < p.x_rows) {
-#pragma unroll
-              for (int j = 0; j < kChunk; ++j) {
-                const int64_t m = static_cast<int64_t>(yt) * BN + c + j;
-                if (m < p.y_rows) {
-                  if (p.out_f32)
-                    reinterpret_cast<float*>(p.C)[m * p.ldc + nn] = to_f32<T>(from_f32<T>(v[j]));
-                  else
-                    reinterpret_cast<T*>(p.C)[m * p.ldc + nn] = from_f32<T>(v[j]);
-                }
+              for (int j = 0; j < kChunk; j += 4) {
+                v[j] += f[i][j >> 2].x; v[j + 1] += f[i][j >> 2].y; v[j + 2] += f[i][j >> 2].z; v[j + 3] += f[i][j >> 2].w;
               }
             }
           }
         }
-        if (!complete && et == 0) p.counters[tile] = 0;  // re-arm for the next launch / graph replay
+        uint32_t r[kChunk];
+        if constexpr (kChunk == 32) tmem_ld_32x32b_x32(taddr + c, r);
+        else tmem_ld_32x32b_x16(taddr + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) v[j] += __uint_as_float(r[j]);
+        store_chunk(xt, yt, c, v);
       }
-      if (complete) {
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[as]);
-      }
+      // re-arm the flags for the next launch / graph replay (each flag has exactly one reader)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int cc = c_first + et; cc < c_last; cc += 128) p.counters[cc] = 0;
     }
   }
 
@@ -451,7 +508,11 @@ int gemm_pair_try(void* C, const void* A, const void* W, int64_t M, int64_t N, i
                   int64_t ldw, int64_t ldc, int dtype, int out_f32, int epilogue, int sms, int panel_mb,
                   cudaStream_t stream);
 
-constexpr int64_t kGemmWsBytes = 48ll << 20;  // stream-K partials: 2 per CTA
+int gemm_pair_decode_try(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_t K, int64_t lda,
+                         int64_t ldw, int64_t ldc, int dtype, int out_f32, int sms, float* ws, int64_t ws_bytes,
+                         int* flags, int n_flags, int max_split, cudaStream_t stream);
+
+constexpr int64_t kGemmWsBytes = 48ll << 20;  // stream-K partials: one [128 x BN] fp32 tile per CTA
 constexpr int kGemmCounters = 4096;
 
 template <typename T, int BN, bool kSwap, int kEpi>
@@ -509,24 +570,30 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
   int rc;
 
   // stream-K grid: one equal unit range per SM, but never so thin that a tile is shared by more
-  // than ~8 CTAs (the fix-up reads one partial per contributor) or a CTA gets < 4 k-blocks
-  // tuning knobs (experiments only): SPD_GEMM_STREAMK=0 disables stream-K, SPD_GEMM_SPLIT=d caps
-  // the contributors per tile at ~d, SPD_GEMM_SWAPMAX=m is the largest M routed to swap-AB
-  // Measured on B200 (scripts/bench_gemm_decode.py, profiles/r01_gemm_decode_sweep.log): one SM
-  // streams ~90-100 GB/s, the global-memory fix-up of a shared tile costs ~8 us, so K is only
-  // split when few tiles would each stream a long K (down_proj: 32 tiles x 224 k-blocks).
+  // than ~SPD_GEMM_SPLIT CTAs (the owner reads one partial per contributor) or a CTA gets < 4
+  // k-blocks.  Tuning knobs (experiments only): SPD_GEMM_STREAMK=0 disables stream-K, =2 forces it;
+  // SPD_GEMM_SPLIT=d caps the contributors per tile at ~d; SPD_GEMM_SWAPMAX=m is the largest M
+  // routed to swap-AB; SPD_GEMM_CLUSTER=1 routes few-tile layers at M <= 128 to the cluster
+  // split-K kernel (gemm_cluster.cu) instead.
   static const int env_streamk = getenv("SPD_GEMM_STREAMK") ? atoi(getenv("SPD_GEMM_STREAMK")) : 1;
   static const int env_split = getenv("SPD_GEMM_SPLIT") ? atoi(getenv("SPD_GEMM_SPLIT")) : 4;
-  static const int env_swapmax = getenv("SPD_GEMM_SWAPMAX") ? atoi(getenv("SPD_GEMM_SWAPMAX")) : 128;
+  static const int env_swapmax = getenv("SPD_GEMM_SWAPMAX") ? atoi(getenv("SPD_GEMM_SWAPMAX")) : 256;
   const bool ws_ok = env_streamk && workspace && workspace_bytes >= spd_gemm_workspace_bytes();
-  const bool can_streamk = ws_ok && (env_streamk == 2 || kblocks >= 128);
   auto streamk_grid = [&](long long tiles, int BN) -> int {
     const long long units = tiles * kblocks;
     long long g = sms;
     const long long min_units = kblocks / env_split > 4 ? kblocks / env_split : 4;
     if (units / g < min_units) g = units / min_units > 0 ? units / min_units : 1;
-    if (g * 2 * kBM * BN * 4 > kGemmWsBytes) g = kGemmWsBytes / (2ll * kBM * BN * 4);
+    if (g * kBM * BN * 4 > kGemmWsBytes) g = kGemmWsBytes / (1ll * kBM * BN * 4);
+    if (g > kGemmCounters) g = kGemmCounters;
     return static_cast<int>(g);
+  };
+  // whole tiles dealt round-robin leave SMs idle in the last wave; stream-K when that costs > 10 %
+  auto wants_streamk = [&](long long tiles) -> bool {
+    if (!ws_ok || kblocks < 8) return false;
+    if (env_streamk == 2) return true;
+    const long long waves = (tiles + sms - 1) / sms;
+    return tiles * 10 < waves * sms * 9;
   };
 
   // y tiles per rasterisation panel: keep ~40 MB of W rows hot in L2 (tile_coords)
@@ -537,22 +604,24 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
     return static_cast<int>(q < 1 ? 1 : q);
   };
 
-  // M <= 128: swap-AB (the token dimension feeds UMMA-N, padded to 16..128).  Beyond that the
-  // re-read of the activation tile by every weight tile dominates, so 128 < M <= 256 runs
-  // un-swapped 128 x 256 tiles (activation traffic = half the weight traffic).
+  // Decode regime, M <= 256: swap-AB.  The token dimension feeds UMMA-N (16, or M rounded up to a
+  // multiple of 32), each 128-row weight tile is read once, and no MMA work is spent on padding
+  // rows (the un-swapped form would pad 160 tokens to 2 x 128 and read W twice from L2).
   const bool swap = (M <= env_swapmax) && epilogue == SPD_EPI_NONE;
   if (swap) {
-    // few weight tiles (W_qkv, W_o, W_down): split K over a thread-block cluster, reduce in DSMEM
+    // 32 < M <= 256: CTA pairs share one activation tile between 256 weight rows (gemm_pair_decode.cu)
+    rc = gemm_pair_decode_try(C, A, W, M, N, K, lda, ldw, ldc, dtype, out_f32, sms, ws_ok ? p.ws : nullptr,
+                              kGemmWsBytes, ws_ok ? p.counters : nullptr, kGemmCounters, env_split, st);
+    if (rc != 1) return rc;
     rc = gemm_cluster_try(C, A, W, M, N, K, lda, ldw, ldc, dtype, out_f32, sms, st);
     if (rc != 1) return rc;
-    int BN = 16;
-    while (BN < M) BN <<= 1;  // 16,32,64 (128, 256 only when SPD_GEMM_SWAPMAX raises the limit)
+    const int BN = M <= 16 ? 16 : static_cast<int>((M + 31) / 32 * 32);
     p.x_rows = N;
     p.y_rows = M;
     p.x_tiles = static_cast<int>((N + kBM - 1) / kBM);
     p.y_tiles = 1;
     int grid = static_cast<int>(p.x_tiles < sms ? p.x_tiles : sms);
-    if (can_streamk && p.x_tiles <= kGemmCounters && (env_streamk == 2 || p.x_tiles * 2 <= sms)) {
+    if (wants_streamk(p.x_tiles)) {
       grid = streamk_grid(p.x_tiles, BN);
       p.streamk = 1;
     }
@@ -566,7 +635,11 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
       SPD_GEMM_SWAP(16)
       SPD_GEMM_SWAP(32)
       SPD_GEMM_SWAP(64)
+      SPD_GEMM_SWAP(96)
       SPD_GEMM_SWAP(128)
+      SPD_GEMM_SWAP(160)
+      SPD_GEMM_SWAP(192)
+      SPD_GEMM_SWAP(224)
       SPD_GEMM_SWAP(256)
     }
 #undef SPD_GEMM_SWAP
@@ -600,9 +673,8 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
     p.panel = panel_for(BN);
     const int total = p.x_tiles * p.y_tiles;
     int grid = total < sms ? total : sms;
-    if (M <= 256 && use256 && can_streamk && total <= kGemmCounters &&
-        (env_streamk == 2 || total * 2 <= sms)) {
-      grid = streamk_grid(total, BN);  // decode regime, un-swapped
+    if (M <= 256 && use256 && wants_streamk(total)) {
+      grid = streamk_grid(total, BN);  // decode regime, un-swapped (fused-epilogue callers only)
       p.streamk = 1;
     }
     if ((rc = get_tmap(&tx, A, M, K, lda, kBM))) return rc;

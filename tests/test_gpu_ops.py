@@ -160,6 +160,33 @@ def test_gemm(ops, dtype, M, N, K):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,N,K", [(33, 256, 512), (40, 4096, 4096), (64, 4096, 14336), (100, 6144, 4096),
+                                   (128, 4096, 4096), (160, 4096, 14336), (192, 28672, 1024),
+                                   (200, 1000, 2048), (256, 6144, 4096), (96, 520, 576), (17, 4096, 4096),
+                                   (32, 6144, 4096), (130, 128256, 512)])
+def test_gemm_decode_regime(ops, dtype, M, N, K):
+    """Swap-AB decode regime: CTA-pair kernel (32 < M <= 256) and single-CTA kernel, whole tiles
+    and stream-K with the owner fix-up, on the whole GPU and on small / odd SM budgets (the decode
+    partition).  Parity with the fp32 matmul of the same 16-bit operands; every schedule must
+    produce bit-identical results run to run."""
+    torch.manual_seed(M * 7 + N + K)
+    a = (torch.randn(M, K) * 0.5).to(dtype)
+    w = (torch.randn(N, K) / math.sqrt(K)).to(dtype)
+    ref = a.float() @ w.float().t()
+    ad, wd = a.to(DEV), w.to(DEV)
+    try:
+        for budget in (0, 76, 20, 7, 2):
+            ops.set_sm_budget(budget)
+            c = ops.linear(ad, wd)
+            err = (c.cpu().float() - ref).abs().max().item()
+            assert err < _tol(dtype, 3e-3, 2.5e-2), (budget, err)
+            for _ in range(3):  # flags / partials are re-armed: replays must match bit for bit
+                assert torch.equal(ops.linear(ad, wd), c), budget
+    finally:
+        ops.set_sm_budget(0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_gemm_fused_silu_mul_and_strides(ops, dtype):
     torch.manual_seed(9)
     M, N, K = 700, 1536, 1024
