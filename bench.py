@@ -247,7 +247,33 @@ def roofline_section(engine, cfg, dtype, tokens_per_prefill_batch, decode_bs, ct
     fl = 4.0 * Hq * D * nreq * E * (E + 1) / 2
     extra["attn_prefill"] = {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": tf_burst * share,
                              "unit": "TFLOP/s", "frac": fl / ms / 1e9 / (tf_burst * share), "launch_ms": ms,
-                             "shape": f"{nreq} x {E} tokens, prefix 0"}
+                             "shape": f"{nreq} x {E} tokens, prefix 0",
+                             "note": f"on the prefill partition ({engine.p_sms} SMs); peak = measured burst x SM share"}
+    # the same kernel alone on the whole device, at the bench shape and at a long-context shape
+    ops.set_sm_budget(0)
+    ms = time_on_stream(lambda: ops.attn_prefill(q, kp, vp, rtt, rpi, pre, ext, st, E, Hq, Hk, D, D ** -0.5),
+                        full_stream, flush=flush)
+    extra["attn_prefill_full_gpu"] = {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": tf_burst,
+                                      "unit": "TFLOP/s", "frac": fl / ms / 1e9 / tf_burst, "launch_ms": ms,
+                                      "shape": f"{nreq} x {E} tokens, prefix 0, all {n_sms} SMs"}
+    E2 = 4096
+    n2 = max(M // E2, 1)
+    kp2 = torch.randn(n2 * E2 + 8, Hk, D, device=dev).to(dtype)
+    vp2 = torch.randn(n2 * E2 + 8, Hk, D, device=dev).to(dtype)
+    rtt2 = (torch.arange(n2 * E2, device=dev, dtype=torch.int32) + 1).view(n2, E2).contiguous()
+    rpi2 = torch.arange(n2, device=dev)
+    pre2 = torch.zeros(n2, dtype=torch.int32, device=dev)
+    ext2 = torch.full((n2,), E2, dtype=torch.int32, device=dev)
+    _, st2 = ops.compute_positions(pre2, ext2, n2 * E2)
+    q2 = torch.randn(n2 * E2, Hq * D, device=dev).to(dtype)
+    ms = time_on_stream(lambda: ops.attn_prefill(q2, kp2, vp2, rtt2, rpi2, pre2, ext2, st2, E2, Hq, Hk, D, D ** -0.5),
+                        full_stream, flush=flush)
+    fl2 = 4.0 * Hq * D * n2 * E2 * (E2 + 1) / 2
+    extra["attn_prefill_full_gpu_4k"] = {"bound": "tensor", "achieved": fl2 / ms / 1e9, "peak": tf_burst,
+                                         "unit": "TFLOP/s", "frac": fl2 / ms / 1e9 / tf_burst, "launch_ms": ms,
+                                         "shape": f"{n2} x {E2} tokens, prefix 0, all {n_sms} SMs"}
+    del kp2, vp2, q2
+    ops.set_sm_budget(engine.p_sms)
     # (3) decode attention (HBM bound) on the decode partition
     ops.set_sm_budget(engine.d_sms)
     B, S = decode_bs, ctx
@@ -264,6 +290,13 @@ def roofline_section(engine, cfg, dtype, tokens_per_prefill_batch, decode_bs, ct
     extra["attn_decode"] = {"bound": "hbm", "achieved": by / ms / 1e6, "peak": hbm, "unit": "GB/s",
                             "frac": by / ms / 1e6 / hbm, "launch_ms": ms, "shape": f"B={B} S={S}",
                             "note": f"decode partition = {engine.d_sms} SMs; peak is the full-device copy bandwidth"}
+    ops.set_sm_budget(0)
+    ms = time_on_stream(lambda: ops.attn_decode(qd, kp, vp, rtt, rpi, sl, Hq, Hk, D, D ** -0.5),
+                        full_stream, iters=20, flush=flush)
+    extra["attn_decode_full_gpu"] = {"bound": "hbm", "achieved": by / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                                     "frac": by / ms / 1e6 / hbm, "launch_ms": ms,
+                                     "shape": f"B={B} S={S}, all {n_sms} SMs"}
+    ops.set_sm_budget(engine.d_sms)
     # (4) decode-regime GEMM (weight streaming, HBM bound)
     xd = (torch.randn(B, H, device=dev) * 0.5).to(dtype)
     ms = time_on_stream(lambda: ops.linear(xd, w), engine.d_stream, iters=20, flush=flush)

@@ -18,9 +18,11 @@ cap() {  # name, kernel regex, script args...
   timeout 300 $NCU --set full --import-source on -k regex:$kern -s 3 -c 1 -f -o $OUT/${TAG}_$name "$@" > $OUT/${TAG}_$name.log 2>&1
   ncu -i $OUT/${TAG}_$name.ncu-rep $RAW > $OUT/${TAG}_$name.raw.csv 2>/dev/null
 }
-cap gemm_gateup gemm_pair python scripts/prof_gemm.py 8192
+cap gemm_gateup gemm_pair_kernel python scripts/prof_gemm.py 8192
 cap attn_prefill_8x1024 attn_prefill python scripts/prof_attn.py prefill 8 1024
 cap attn_prefill_2x4096 attn_prefill python scripts/prof_attn.py prefill 2 4096
 cap attn_decode_64x1088 attn_decode python scripts/prof_attn.py decode 64 1088
 cap attn_decode_160x1088 attn_decode python scripts/prof_attn.py decode 160 1088
+cap gemm_decode_qkv_m128 gemm_pair_decode python scripts/prof_gemm_decode.py 128 6144 4096
+cap gemm_decode_gateup_m128 gemm_pair_decode python scripts/prof_gemm_decode.py 128 28672 4096
 ls -la $OUT
