@@ -137,8 +137,12 @@ int spd_write_req_to_token(int32_t* req_to_token, const int64_t* req_pool_indice
  * epilogue: SPD_EPI_NONE, or SPD_EPI_SILU_MUL: W is [2N, K] (gate rows || up rows, the
  * MergedColumnParallelLinear order, S/models/llama.py:67-73) and C[M,N] = silu(A Wg^T) * (A Wu^T),
  * both products rounded to dtype first (== gate_up_proj followed by SiluAndMul).
- * workspace: device scratch for split-K partials (spd_gemm_workspace_bytes()); may be NULL when
- * the call does not split.
+ * workspace: device scratch for the stream-K partials and their "published" flags
+ * (spd_gemm_workspace_bytes()), zero-initialised ONCE by the caller and then owned by one stream
+ * (the kernels re-arm the flags themselves; two streams must not share one workspace).  May be
+ * NULL: the call then never splits a tile.
+ * sm_budget: number of SMs the call may occupy (0 = all); a worker running on a green-context
+ * partition passes its partition's SM count so that persistent grids and the stream-K split match it.
  * ------------------------------------------------------------------------------------------- */
 #define SPD_EPI_NONE 0
 #define SPD_EPI_SILU_MUL 1
