@@ -14,7 +14,10 @@ Pinning (see tests/test_oracle_golden.py and tests/golden/make_golden.py):
     reference's kernel tests (sgl-kernel/tests/test_norm.py:8-50, test_activation.py:8-16,
     test_rotary_embedding.py:9-128);
   * the end-to-end model wiring (models/llama.py) has no stored golden vector in the reference
-    (needs HF weights) — whole-model parity is "unpinned" beyond the per-op pins above.
+    (its own whole-model test compares SRT with the HuggingFace runner and needs downloaded
+    weights); it is pinned the same way here: tests/test_oracle_vs_hf.py checks the oracle's
+    logits against transformers' LlamaForCausalLM on identical random weights (prefill, ragged
+    batch, chunked prefill with a prefix, paged decode, Llama-3.1 rope scaling; max-abs < 2e-4).
 
 Two arithmetic modes:
   * compute="native": every op runs in the model dtype exactly as torch-eager on CPU would
