@@ -1,7 +1,7 @@
-"""Per-op time of one Llama-3-8B decoder layer at a prefill batch of 8 x 1024 tokens, on the
+"""Per-op time of one Llama-3-8B decoder layer at a prefill batch of n x 1024 tokens, on the
 prefill green-context partition (or the whole GPU), CUDA events on the launching stream.
 Answers "where does a prefill layer's time go on the partition" (no ncu under green contexts).
-usage: python scripts/bench_prefill_ops.py [prefill_pct=50 | 100]"""
+usage: python scripts/bench_prefill_ops.py [prefill_pct=50 | 100] [n_requests=8]"""
 import sys
 
 import torch
@@ -13,7 +13,8 @@ from semi_pd_b200.forward_batch_info import ForwardBatch, ForwardMode, ModelWork
 from semi_pd_b200.model_runner import ModelRunner  # noqa: E402
 
 pct = int(sys.argv[1]) if len(sys.argv) > 1 else 50
-NREQ, EXT = 8, 1024
+NREQ = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+EXT = 1024
 T = NREQ * EXT
 cfg = get_model_config("llama-3-8b")
 cfg.num_hidden_layers = 2

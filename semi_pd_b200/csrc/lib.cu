@@ -135,17 +135,21 @@ int spd_partition_create(int device, int prefill_sms, int decode_sms, spd_partit
   SPD_REQUIRE(prefill_sms + decode_sms <= total, SPD_E_BADARG,
               "spd_partition_create: %d + %d SMs exceed the device's %d", prefill_sms, decode_sms,
               total);
-  // carve the prefill group first, then the decode group out of what remains
+  // Groups come in multiples of the device's SM granularity (8 on sm_100); the group whose
+  // request is such a multiple is carved first and the other one gets exactly what remains (so a
+  // 76 + 72 split of 148 SMs is expressible either way round).
+  const int first = (prefill_sms % 8 != 0 && decode_sms % 8 == 0) ? 1 : 0;
+  const int want[2] = {prefill_sms, decode_sms};
   CUdevResource grp[2], rem0, rem1;
   unsigned int n = 1;
-  r = split(&grp[0], &n, &all, &rem0, 0, (unsigned)prefill_sms);
+  r = split(&grp[first], &n, &all, &rem0, 0, (unsigned)want[first]);
   SPD_REQUIRE(r == CUDA_SUCCESS && n == 1, SPD_E_DRIVER,
-              "cuDevSmResourceSplitByCount(prefill=%d) failed (%d)", prefill_sms, (int)r);
+              "cuDevSmResourceSplitByCount(%d) failed (%d)", want[first], (int)r);
   n = 1;
-  r = split(&grp[1], &n, &rem0, &rem1, 0, (unsigned)decode_sms);
+  r = split(&grp[1 - first], &n, &rem0, &rem1, 0, (unsigned)want[1 - first]);
   if (r != CUDA_SUCCESS || n != 1) {
-    // the remainder is smaller than the rounded-up request: give decode everything that is left
-    grp[1] = rem0;
+    // the remainder is smaller than the rounded-up request: the second group is everything left
+    grp[1 - first] = rem0;
   }
   spd_partition* p = new spd_partition();
   p->device = device;

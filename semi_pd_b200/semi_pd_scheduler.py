@@ -481,9 +481,12 @@ class SemiPDEngine:
         if partition == "green":
             # the reference's caps overlap (80 % + 100 %); green contexts are disjoint, so the two
             # percentages are normalised to a split of the device
-            p_sms = max(8, int(round(total * p_pct / float(p_pct + d_pct) / 8.0)) * 8)
-            p_sms = min(p_sms, total - 8)
-            self.partition = ops.SmPartition(gpu_id, p_sms, total - p_sms)
+            # groups are multiples of 8 SMs and 148 is not: the decode group is rounded to the
+            # granularity and the prefill group gets what remains (50/50 -> 76 + 72; prefill is
+            # the throughput-bound side of a long-prompt mix)
+            d_sms = max(8, int(total * d_pct / float(p_pct + d_pct) / 8.0 + 0.5) * 8)
+            d_sms = min(d_sms, total - 8)
+            self.partition = ops.SmPartition(gpu_id, total - d_sms, d_sms)
             self.p_stream, self.d_stream = self.partition.prefill_stream, self.partition.decode_stream
             self.p_sms, self.d_sms = self.partition.prefill_sms, self.partition.decode_sms
         elif partition == "none":
