@@ -291,18 +291,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
           }
         }
       } else {
-        // swapped: lane index runs along N (contiguous in C), column j is the token
+        // swapped: lane index runs along N (contiguous in C), column j is the token.  The type
+        // branch and the address arithmetic are hoisted: one predicated store per element (the
+        // per-element form compiled to ~24 instructions per 2-byte store).
         const int64_t nn = static_cast<int64_t>(xt) * kBM + row;
         if (nn < p.x_rows) {
+          const int m0 = yt * BN + c;
+          const int m_left = static_cast<int>(p.y_rows) - m0;  // tokens of this chunk that exist
+          if (p.out_f32) {
+            float* dst = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(m0) * p.ldc + nn;
 #pragma unroll
-          for (int j = 0; j < kChunk; ++j) {
-            const int64_t m = static_cast<int64_t>(yt) * BN + c + j;
-            if (m < p.y_rows) {
-              if (p.out_f32)
-                reinterpret_cast<float*>(p.C)[m * p.ldc + nn] = to_f32<T>(from_f32<T>(v[j]));
-              else
-                reinterpret_cast<T*>(p.C)[m * p.ldc + nn] = from_f32<T>(v[j]);
-            }
+            for (int j = 0; j < kChunk; ++j)
+              if (j < m_left) dst[static_cast<int64_t>(j) * p.ldc] = to_f32<T>(from_f32<T>(v[j]));
+          } else {
+            T* dst = reinterpret_cast<T*>(p.C) + static_cast<int64_t>(m0) * p.ldc + nn;
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j)
+              if (j < m_left) dst[static_cast<int64_t>(j) * p.ldc] = from_f32<T>(v[j]);
           }
         }
       }

@@ -178,15 +178,17 @@ gemm_cluster_splitk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid
           }
         }
         if (nn < p.n_rows) {
+          const int m_left = static_cast<int>(p.m_rows) - c;  // tokens of this chunk that exist
+          if (p.out_f32) {
+            float* dst = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(c) * p.ldc + nn;
 #pragma unroll
-          for (int j = 0; j < kChunk; ++j) {
-            const int64_t m = c + j;
-            if (m < p.m_rows) {
-              if (p.out_f32)
-                reinterpret_cast<float*>(p.C)[m * p.ldc + nn] = to_f32<T>(from_f32<T>(v[j]));
-              else
-                reinterpret_cast<T*>(p.C)[m * p.ldc + nn] = from_f32<T>(v[j]);
-            }
+            for (int j = 0; j < kChunk; ++j)
+              if (j < m_left) dst[static_cast<int64_t>(j) * p.ldc] = to_f32<T>(from_f32<T>(v[j]));
+          } else {
+            T* dst = reinterpret_cast<T*>(p.C) + static_cast<int64_t>(c) * p.ldc + nn;
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j)
+              if (j < m_left) dst[static_cast<int64_t>(j) * p.ldc] = from_f32<T>(v[j]);
           }
         }
       }
