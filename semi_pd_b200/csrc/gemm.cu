@@ -38,7 +38,7 @@ namespace spd {
 constexpr int kGemmThreads = 256;
 constexpr int kBM = 128;  // UMMA M (TMEM lanes)
 constexpr int kBK = 64;   // one 128-byte swizzle atom of 16-bit elements
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr int kSmemBudget = 220 * 1024;
 
 struct GemmParams {

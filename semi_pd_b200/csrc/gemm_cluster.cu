@@ -40,7 +40,7 @@ template <int BN>
 __host__ __device__ constexpr int cg_stage_bytes() { return (kCgBM + BN) * kCgBK * 2; }
 template <int BN>
 __host__ __device__ constexpr int cg_stages() {
-  return (kCgSmemBudget / cg_stage_bytes<BN>()) < 8 ? (kCgSmemBudget / cg_stage_bytes<BN>()) : 8;
+  return (kCgSmemBudget / cg_stage_bytes<BN>()) < 12 ? (kCgSmemBudget / cg_stage_bytes<BN>()) : 12;
 }
 template <int BN>
 __host__ __device__ constexpr int cg_smem_bytes() { return cg_stages<BN>() * cg_stage_bytes<BN>() + 1024 + 256; }

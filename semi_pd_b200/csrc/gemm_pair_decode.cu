@@ -47,7 +47,7 @@ template <int BN>
 __host__ __device__ constexpr int pd_stage_bytes() { return kPdWBytes + (BN / 2) * kPdBK * 2; }
 template <int BN>
 __host__ __device__ constexpr int pd_stages() {
-  return (kPdSmemBudget / pd_stage_bytes<BN>()) < 8 ? (kPdSmemBudget / pd_stage_bytes<BN>()) : 8;
+  return (kPdSmemBudget / pd_stage_bytes<BN>()) < 12 ? (kPdSmemBudget / pd_stage_bytes<BN>()) : 12;
 }
 template <int BN>
 __host__ __device__ constexpr int pd_smem_bytes() {
