@@ -129,6 +129,20 @@ int spd_write_req_to_token(int32_t* req_to_token, const int64_t* req_pool_indice
                            int64_t req_to_token_stride, spd_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * OPT-family ops (BASELINE configs[0]: opt-125m plumbing + logit check).  The reference has no OPT
+ * model; these follow torch.nn.LayerNorm / F.relu / the `residual + hidden_states` adds of
+ * transformers' modeling_opt.py (OPTDecoderLayer.forward), fp32 math, 16-bit I/O.
+ * spd_layernorm: out = (x - mean) / sqrt(var + eps) * gamma + beta per row (dim <= 8192).
+ * spd_bias_act_residual: out = act(x + bias) + residual, rows contiguous; bias / residual may be
+ * NULL; act: 0 = identity, 1 = ReLU.  out may alias x.
+ * ------------------------------------------------------------------------------------------- */
+int spd_layernorm(void* out, const void* x, const void* gamma, const void* beta, int64_t tokens,
+                  int64_t dim, int64_t x_stride, int64_t out_stride, float eps, int dtype,
+                  spd_stream_t stream);
+int spd_bias_act_residual(void* out, const void* x, const void* bias, const void* residual,
+                          int64_t tokens, int64_t dim, int act, int dtype, spd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * GEMM — C[M,N] = A[M,K] * W[N,K]^T, 16-bit inputs, fp32 accumulation in TMEM (tcgen05 + TMA).
  * replaces UnquantizedLinearMethod.apply = F.linear (S/layers/linear.py:165-172) for
  * W_qkv / W_o / W_gate_up / W_down and the lm_head matmul (S/layers/logits_processor.py:416-419).

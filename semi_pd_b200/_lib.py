@@ -38,6 +38,8 @@ SIGNATURES = {
     "spd_rmsnorm": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _f, _i, _p]),
     "spd_fused_add_rmsnorm": (_i, [_p, _p, _p, _i64, _i64, _f, _i, _p]),
     "spd_silu_and_mul": (_i, [_p, _p, _i64, _i64, _i, _p]),
+    "spd_layernorm": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _f, _i, _p]),
+    "spd_bias_act_residual": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _i, _p]),
     "spd_rope_inplace": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i64, _i64, _i, _i, _p]),
     "spd_rope_kvwrite": (
         _i,

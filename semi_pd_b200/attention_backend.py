@@ -98,8 +98,9 @@ class SpdAttnBackend(AttentionBackend):
         self.device = model_runner.device
         self.num_q_heads = model_runner.model_config.num_attention_heads // model_runner.tp_size
         self.head_dim = model_runner.model_config.head_dim
-        # "tc" = tcgen05 kernels (the product path); "simt" exists for bring-up / cross-checks only
-        self.impl = os.environ.get("SPD_ATTN_IMPL", "tc")
+        # "tc" = tcgen05 kernels (the product path, head_dim 128); "simt" exists for bring-up /
+        # cross-checks and serves the head_dim-64 plumbing model (OPT-125m, BASELINE configs[0])
+        self.impl = os.environ.get("SPD_ATTN_IMPL", "tc" if self.head_dim == 128 else "simt")
         self.max_extend_len = 0
         self.decode_workspace = None
 

@@ -41,6 +41,9 @@ class ModelConfig:
     tie_word_embeddings: bool = False
     hidden_act: str = "silu"
     is_encoder_decoder: bool = False
+    # "llama" (models/llama.py) or "opt" (BASELINE configs[0]: pre-LN, learned positions, ReLU, biases)
+    model_type: str = "llama"
+    layer_norm_eps: float = 1e-5
 
     @property
     def context_len(self) -> int:
@@ -62,6 +65,10 @@ _PRESETS = {
     "tiny-llama-test": dict(hidden_size=256, intermediate_size=512, num_hidden_layers=2,
                             num_attention_heads=4, num_key_value_heads=2, head_dim=128,
                             vocab_size=1024, max_position_embeddings=2048),
+    # BASELINE configs[0]: facebook/opt-125m (hand-written config, no weights offline)
+    "opt-125m": dict(model_type="opt", hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                     num_attention_heads=12, num_key_value_heads=12, head_dim=64, vocab_size=50272,
+                     max_position_embeddings=2048, hidden_act="relu", tie_word_embeddings=True),
     # one 8B-shaped layer pair: exhaustive parity at real head/FFN shapes
     "llama-3-8b-2layer": dict(num_hidden_layers=2, vocab_size=4096),
 }

@@ -426,6 +426,94 @@ write_req_to_token_kernel(int32_t* __restrict__ req_to_token, const int64_t* __r
   for (int64_t j = threadIdx.x; j < seq - pre; j += blockDim.x) dst[j] = static_cast<int32_t>(src[j]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// OPT-family ops (BASELINE configs[0], the plumbing model): LayerNorm with bias, and
+// y = act(x + bias) + residual.  fp32 math, 16-bit I/O, 16-byte vectors.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int kMaxVec>
+__global__ void __launch_bounds__(kNormThreads)
+layernorm_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ gamma,
+                 const T* __restrict__ beta, int64_t dim, int64_t x_stride, int64_t out_stride, float eps) {
+  __shared__ float red[33];
+  griddep_wait();
+  const int64_t row = blockIdx.x;
+  const int nvec = static_cast<int>(dim >> 3);
+  const Vec8* xr = reinterpret_cast<const Vec8*>(x + row * x_stride);
+  float vals[kMaxVec][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+    if (v < nvec) {
+      vec8_to_f32<T>(xr[v], vals[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += vals[i][j];
+    }
+  }
+  const float mean = block_sum(s, red) / static_cast<float>(dim);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = vals[i][j] - mean;
+        ss += d * d;
+      }
+    }
+  }
+  __syncthreads();  // `red` is reused
+  const float inv = rsqrtf(block_sum(ss, red) / static_cast<float>(dim) + eps);
+  griddep_launch_dependents();
+  Vec8* orow = reinterpret_cast<Vec8*>(out + row * out_stride);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+    if (v < nvec) {
+      float g[8], b[8], o[8];
+      vec8_to_f32<T>(reinterpret_cast<const Vec8*>(gamma)[v], g);
+      vec8_to_f32<T>(reinterpret_cast<const Vec8*>(beta)[v], b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (vals[i][j] - mean) * inv * g[j] + b[j];
+      orow[v] = f32_to_vec8<T>(o);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_act_residual_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ bias,
+                         const T* __restrict__ residual, int64_t tokens, int64_t dim, int act) {
+  griddep_wait();
+  const int64_t nvec_row = dim >> 3;
+  const int64_t total = tokens * nvec_row;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t c = i % nvec_row;
+    float f[8];
+    vec8_to_f32<T>(reinterpret_cast<const Vec8*>(x)[i], f);
+    if (bias) {
+      float b[8];
+      vec8_to_f32<T>(reinterpret_cast<const Vec8*>(bias)[c], b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += b[j];
+    }
+    if (act == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (residual) {
+      float r[8];
+      vec8_to_f32<T>(reinterpret_cast<const Vec8*>(residual)[i], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    }
+    reinterpret_cast<Vec8*>(out)[i] = f32_to_vec8<T>(f);
+  }
+  griddep_launch_dependents();
+}
+
 }  // namespace spd
 
 using namespace spd;
@@ -630,6 +718,41 @@ int spd_write_req_to_token(int32_t* req_to_token, const int64_t* req_pool_indice
       req_to_token, req_pool_indices, pre_lens, seq_lens, extend_lens, out_cache_loc,
       req_to_token_stride);
   SPD_CHECK_LAUNCH("write_req_to_token_kernel");
+  return 0;
+}
+
+int spd_layernorm(void* out, const void* x, const void* gamma, const void* beta, int64_t tokens, int64_t dim,
+                  int64_t x_stride, int64_t out_stride, float eps, int dtype, spd_stream_t stream) {
+  SPD_REQUIRE(out && x && gamma && beta, SPD_E_BADARG, "spd_layernorm: null pointer");
+  SPD_REQUIRE(tokens >= 0 && dim > 0 && dim <= 8192, SPD_E_SHAPE,
+              "spd_layernorm: bad sizes tokens=%lld dim=%lld (dim <= 8192)", (long long)tokens, (long long)dim);
+  SPD_REQUIRE(dim % 8 == 0 && x_stride % 8 == 0 && out_stride % 8 == 0 && aligned16(out) && aligned16(x) &&
+                  aligned16(gamma) && aligned16(beta),
+              SPD_E_ALIGN, "spd_layernorm: dim/strides must be multiples of 8 and pointers 16-B aligned");
+  if (tokens == 0) return 0;
+  SPD_DISPATCH_DTYPE(dtype, {
+    SPD_CUDA(launch(layernorm_kernel<T, 4>, dim3((unsigned)tokens), dim3(kNormThreads), 0, as_stream(stream),
+                    pdl_enabled(), (T*)out, (const T*)x, (const T*)gamma, (const T*)beta, dim, x_stride,
+                    out_stride, eps));
+  });
+  return 0;
+}
+
+int spd_bias_act_residual(void* out, const void* x, const void* bias, const void* residual, int64_t tokens,
+                          int64_t dim, int act, int dtype, spd_stream_t stream) {
+  SPD_REQUIRE(out && x, SPD_E_BADARG, "spd_bias_act_residual: null pointer");
+  SPD_REQUIRE(tokens >= 0 && dim > 0 && (act == 0 || act == 1), SPD_E_BADARG, "spd_bias_act_residual: bad arguments");
+  SPD_REQUIRE(dim % 8 == 0 && aligned16(out) && aligned16(x) && (!bias || aligned16(bias)) &&
+                  (!residual || aligned16(residual)),
+              SPD_E_ALIGN, "spd_bias_act_residual: dim must be a multiple of 8 and pointers 16-B aligned");
+  if (tokens == 0) return 0;
+  int64_t blocks = (tokens * (dim >> 3) + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(device_sm_count_cached()) * 16;
+  if (blocks > cap) blocks = cap;
+  SPD_DISPATCH_DTYPE(dtype, {
+    SPD_CUDA(launch(bias_act_residual_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream),
+                    pdl_enabled(), (T*)out, (const T*)x, (const T*)bias, (const T*)residual, tokens, dim, act));
+  });
   return 0;
 }
 

@@ -89,7 +89,11 @@ class ModelRunner:
     # model + memory
     # ------------------------------------------------------------------------------------------
     def load_model(self):
-        self.model = LlamaForCausalLM(self.model_config, dtype=self.dtype, device=self.device)
+        if getattr(self.model_config, "model_type", "llama") == "opt":
+            from .opt import OPTForCausalLM
+            self.model = OPTForCausalLM(self.model_config, dtype=self.dtype, device=self.device)
+        else:
+            self.model = LlamaForCausalLM(self.model_config, dtype=self.dtype, device=self.device)
         if self.server_args.load_format == "dummy":
             self.model.init_dummy_weights(self.server_args.random_seed)
         elif self.server_args.load_format != "external":

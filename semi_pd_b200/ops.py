@@ -98,6 +98,37 @@ def silu_and_mul(input: torch.Tensor, out: Optional[torch.Tensor] = None) -> tor
     return out
 
 
+def layernorm(input: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """torch.nn.LayerNorm over the last dimension (OPT; transformers modeling_opt.py)."""
+    _cuda(input, weight, bias)
+    d = input.shape[-1]
+    x2 = input.view(-1, d)
+    if x2.stride(1) != 1:
+        raise RuntimeError("layernorm: input must have a contiguous last dimension")
+    if out is None:
+        out = torch.empty((x2.shape[0], d), device=input.device, dtype=input.dtype)
+    check(lib.spd_layernorm(out.data_ptr(), x2.data_ptr(), weight.data_ptr(), bias.data_ptr(), x2.shape[0], d,
+                            x2.stride(0), out.stride(0), float(eps), _dt(input), _stream()), "spd_layernorm")
+    return out.view(input.shape)
+
+
+def bias_act_residual(x: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                      residual: Optional[torch.Tensor] = None, act: str = "none",
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = act(x + bias) + residual, act in {"none", "relu"}; x / residual contiguous."""
+    _cuda(x)
+    if not x.is_contiguous() or (residual is not None and not residual.is_contiguous()):
+        raise RuntimeError("bias_act_residual: x and residual must be contiguous")
+    d = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.spd_bias_act_residual(out.data_ptr(), x.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                    residual.data_ptr() if residual is not None else None, x.numel() // d, d,
+                                    {"none": 0, "relu": 1}[act], _dt(x), _stream()), "spd_bias_act_residual")
+    return out
+
+
 def apply_rope_with_cos_sin_cache_inplace(positions: torch.Tensor, query: torch.Tensor,
                                           key: torch.Tensor, head_size: int,
                                           cos_sin_cache: torch.Tensor, is_neox: bool = True) -> None:

@@ -51,8 +51,10 @@ def test_cuda_graph_batch_sizes_and_presets():
     assert (c.hidden_size, c.num_hidden_layers, c.num_key_value_heads, c.vocab_size) == (4096, 32, 8, 128256)
     assert get_model_config("llama-3-70b").get_num_kv_heads(8) == 1
     assert get_model_config("llama-3-70b").get_num_kv_heads(16) == 1  # replicated when tp > n_kv
+    o = get_model_config("facebook/opt-125m")  # BASELINE configs[0]
+    assert (o.model_type, o.hidden_size, o.num_hidden_layers, o.head_dim, o.vocab_size) == ("opt", 768, 12, 64, 50272)
     with pytest.raises(ValueError):
-        get_model_config("opt-125m")
+        get_model_config("gpt2")
     sa = ServerArgs(enable_semi_pd=True)
     assert sa.disable_radix_cache and sa.chunked_prefill_size == 8192
 
