@@ -160,7 +160,10 @@ def load_peaks():
         return 6650.0, 1590.0, 1400.0, "fallback"
 
 
-def time_on_stream(fn, stream, iters=10, warm=3, flush=None):
+def time_on_stream(fn, stream, iters=10, warm=3, flush=None, burst=1):
+    """Average launch duration, CUDA events on the launching stream.  `burst` launches are timed
+    between one event pair (for kernels of ~100 us, whose working set exceeds L2 by itself, the
+    event / launch gap of a single timed launch is several percent of the kernel)."""
     with torch.cuda.stream(stream):
         for _ in range(warm):
             fn()
@@ -170,11 +173,12 @@ def time_on_stream(fn, stream, iters=10, warm=3, flush=None):
                 flush.add_(1)  # > L2-sized write between timed launches
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            fn()
+            for _ in range(burst):
+                fn()
             e1.record(stream)
             e1.synchronize()
             total += e0.elapsed_time(e1)
-    return total / iters
+    return total / iters / burst
 
 
 def roofline_section(engine, cfg, dtype, tokens_per_prefill_batch, decode_bs, ctx):
@@ -285,17 +289,19 @@ def roofline_section(engine, cfg, dtype, tokens_per_prefill_batch, decode_bs, ct
     sl = torch.full((B,), S, dtype=torch.int64, device=dev)
     qd = torch.randn(B, Hq * D, device=dev).to(dtype)
     ms = time_on_stream(lambda: ops.attn_decode(qd, kp, vp, rtt, rpi, sl, Hq, Hk, D, D ** -0.5),
-                        engine.d_stream, iters=20, flush=flush)
+                        engine.d_stream, iters=10, flush=flush, burst=4)
     by = B * S * Hk * D * 2 * 2 + 2 * B * Hq * D * 2 + 4 * B * S
     extra["attn_decode"] = {"bound": "hbm", "achieved": by / ms / 1e6, "peak": hbm, "unit": "GB/s",
                             "frac": by / ms / 1e6 / hbm, "launch_ms": ms, "shape": f"B={B} S={S}",
-                            "note": f"decode partition = {engine.d_sms} SMs; peak is the full-device copy bandwidth"}
+                            "note": f"decode partition = {engine.d_sms} SMs; peak is the full-device copy bandwidth; "
+                                    "4 launches per event pair (each streams > 2 x L2 of K/V, no reuse)"}
     ops.set_sm_budget(0)
     ms = time_on_stream(lambda: ops.attn_decode(qd, kp, vp, rtt, rpi, sl, Hq, Hk, D, D ** -0.5),
-                        full_stream, iters=20, flush=flush)
+                        full_stream, iters=10, flush=flush, burst=4)
     extra["attn_decode_full_gpu"] = {"bound": "hbm", "achieved": by / ms / 1e6, "peak": hbm, "unit": "GB/s",
                                      "frac": by / ms / 1e6 / hbm, "launch_ms": ms,
-                                     "shape": f"B={B} S={S}, all {n_sms} SMs"}
+                                     "shape": f"B={B} S={S}, all {n_sms} SMs",
+                                     "note": "4 launches per event pair (each streams > 2 x L2 of K/V, no reuse)"}
     ops.set_sm_budget(engine.d_sms)
     # (4) decode-regime GEMM (weight streaming, HBM bound)
     xd = (torch.randn(B, H, device=dev) * 0.5).to(dtype)
