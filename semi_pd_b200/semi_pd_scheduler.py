@@ -461,6 +461,20 @@ class SemiPDDecodeScheduler(SemiPDScheduler):
         self._drain_results(all_of_them=True)
 
 
+def split_sms(total: int, prefill_pct: int, decode_pct: int, granularity: int = 8):
+    """Disjoint (prefill, decode) SM counts for the two green contexts.  The reference's caps are
+    percentages that may overlap (80 % + 100 % by default, python/sglang/semi_pd/utils.py:10-11);
+    here they are normalised to a split of the device.  Groups come in multiples of `granularity`
+    SMs and 148 is not one: the decode group is rounded to the granularity and the prefill group
+    gets what remains (50/50 -> 76 + 72; prefill is the throughput-bound side of a long-prompt
+    mix).  Both sides always get at least one granule."""
+    if prefill_pct <= 0 or decode_pct <= 0:
+        raise ValueError("SM percentages must be positive")
+    d = int(total * decode_pct / float(prefill_pct + decode_pct) / granularity + 0.5) * granularity
+    d = min(max(d, granularity), total - granularity)
+    return total - d, d
+
+
 class SemiPDEngine:
     """`_launch_semi_pd_subprocesses` (entrypoints/engine.py:540-728) for one GPU: builds the D
     worker (weights + pools + CUDA graphs), the P worker (adopts D's parameters through the
@@ -481,12 +495,8 @@ class SemiPDEngine:
         if partition == "green":
             # the reference's caps overlap (80 % + 100 %); green contexts are disjoint, so the two
             # percentages are normalised to a split of the device
-            # groups are multiples of 8 SMs and 148 is not: the decode group is rounded to the
-            # granularity and the prefill group gets what remains (50/50 -> 76 + 72; prefill is
-            # the throughput-bound side of a long-prompt mix)
-            d_sms = max(8, int(total * d_pct / float(p_pct + d_pct) / 8.0 + 0.5) * 8)
-            d_sms = min(d_sms, total - 8)
-            self.partition = ops.SmPartition(gpu_id, total - d_sms, d_sms)
+            p_sms, d_sms = split_sms(total, p_pct, d_pct)
+            self.partition = ops.SmPartition(gpu_id, p_sms, d_sms)
             self.p_stream, self.d_stream = self.partition.prefill_stream, self.partition.decode_stream
             self.p_sms, self.d_sms = self.partition.prefill_sms, self.partition.decode_sms
         elif partition == "none":

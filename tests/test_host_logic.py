@@ -152,3 +152,17 @@ def test_bench_workload_generator_matches_bench_serving_recipe():
     gaps = np.diff([0.0] + arr)
     assert abs(gaps.mean() - 0.1) < 0.01 and all(g >= 0 for g in gaps)
     assert bench.poisson_arrivals(3, float("inf")) == [0.0, 0.0, 0.0]
+
+
+def test_split_sms_normalises_the_reference_percentages():
+    from semi_pd_b200.semi_pd_scheduler import split_sms
+    assert split_sms(148, 50, 50) == (76, 72)
+    assert split_sms(148, 80, 100) == (68, 80)          # the reference's default caps, normalised
+    for p in (20, 35, 65, 80):
+        ps, ds = split_sms(148, p, 100 - p)
+        assert ps + ds == 148 and ds % 8 == 0 and ps >= 8 and ds >= 8
+    assert split_sms(148, 1, 99) == (8, 140) and split_sms(148, 99, 1) == (140, 8)
+    assert split_sms(132, 50, 50) == (68, 64)
+    import pytest as _pt
+    with _pt.raises(ValueError):
+        split_sms(148, 0, 100)
