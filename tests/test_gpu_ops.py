@@ -197,7 +197,7 @@ def test_gemm_fused_silu_mul_and_strides(ops, dtype):
     out = ops.linear(a.to(DEV), w.to(DEV), epilogue=ops.SPD_EPI_SILU_MUL).cpu().float()
     assert (out - ref).abs().max().item() < _tol(dtype, 4e-3, 3e-2)
     # same through the CTA-pair kernel (M a multiple of 256) and through the single-CTA kernel
-    for M2 in (1024, 640):
+    for M2 in (1024, 640, 100, 8):  # pair kernel, single-CTA kernel, and the small-M fused form
         a2 = (torch.randn(M2, K) * 0.5).to(dtype)
         gu2 = torch.nn.functional.linear(a2.float(), w.float()).to(dtype)
         ref2 = O.silu_and_mul(gu2, fp32_math=True).float()
