@@ -21,6 +21,7 @@ random weights (the implementation the reference's own generation tests compare 
 attention paths, ragged prefill, chunked prefill with a cached prefix and paged decode."""
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -48,6 +49,8 @@ class DeepseekOracleConfig:
     rms_norm_eps: float = 1e-6
     rope_theta: float = 10000.0
     max_position_embeddings: int = 4096
+    # {"factor", "beta_fast", "beta_slow", "mscale", "mscale_all_dim", "original_max_position_embeddings"}
+    rope_scaling: Optional[dict] = None
 
 
 def _rms(x, w, eps):
@@ -55,13 +58,42 @@ def _rms(x, w, eps):
     return (v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps)) * w.float()
 
 
-def _rope_interleaved(x, positions, theta):
-    """GPT-J style: pairs (2i, 2i+1) rotate by position * theta^(-2i/d)  (rotary_embedding.py:88-141
+def _yarn_get_mscale(scale: float, mscale: float) -> float:
+    """rotary_embedding.py:627-630."""
+    return 1.0 if scale <= 1 else 0.1 * mscale * math.log(scale) + 1.0
+
+
+def rope_inv_freq(rotary_dim: int, theta: float, rope_scaling: Optional[dict]):
+    """-> (inv_freq [rotary_dim/2], cos/sin magnitude).  Plain RoPE, or the reference's
+    `DeepseekScalingRotaryEmbedding` (rotary_embedding.py:633-708): YaRN blend of interpolated and
+    extrapolated frequencies over the correction range (:377-413), cos / sin scaled by
+    mscale(factor, mscale) / mscale(factor, mscale_all_dim)."""
+    pos_freqs = theta ** (torch.arange(0, rotary_dim, 2, dtype=torch.float32) / rotary_dim)
+    if not rope_scaling:
+        return 1.0 / pos_freqs, 1.0
+    f = float(rope_scaling["factor"])
+    orig = rope_scaling["original_max_position_embeddings"]
+    beta_fast, beta_slow = rope_scaling.get("beta_fast", 32), rope_scaling.get("beta_slow", 1)
+
+    def corr_dim(rot):
+        return (rotary_dim * math.log(orig / (rot * 2 * math.pi))) / (2 * math.log(theta))
+
+    low, high = max(math.floor(corr_dim(beta_fast)), 0), min(math.ceil(corr_dim(beta_slow)), rotary_dim - 1)
+    if low == high:
+        high += 0.001
+    ramp = torch.clamp((torch.arange(rotary_dim // 2, dtype=torch.float32) - low) / (high - low), 0, 1)
+    mask = 1 - ramp
+    inv = (1.0 / (f * pos_freqs)) * (1 - mask) + (1.0 / pos_freqs) * mask
+    mag = _yarn_get_mscale(f, float(rope_scaling.get("mscale", 1))) / _yarn_get_mscale(
+        f, float(rope_scaling.get("mscale_all_dim", 0)))
+    return inv, mag
+
+
+def _rope_interleaved(x, positions, inv_freq, mag=1.0):
+    """GPT-J style: pairs (2i, 2i+1) rotate by position * inv_freq[i]  (rotary_embedding.py:88-141
     with is_neox_style=False)."""
-    d = x.shape[-1]
-    inv = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
-    ang = positions.float()[:, None] * inv[None, :]          # [T, d/2]
-    cos, sin = ang.cos()[:, None, :], ang.sin()[:, None, :]  # broadcast over heads
+    ang = positions.float()[:, None] * inv_freq[None, :]     # [T, d/2]
+    cos, sin = (ang.cos() * mag)[:, None, :], (ang.sin() * mag)[:, None, :]  # broadcast over heads
     x1, x2 = x[..., 0::2], x[..., 1::2]
     out = torch.empty_like(x)
     out[..., 0::2] = x1 * cos - x2 * sin
@@ -79,6 +111,11 @@ class DeepseekOracle:
         self.kv = [torch.zeros(kv_slots + 1, 1, L) for _ in range(cfg.num_hidden_layers)]
         self.req_to_token = torch.zeros(max_reqs, max_ctx, dtype=torch.int32)
         self.scaling = (cfg.qk_nope_head_dim + cfg.qk_rope_head_dim) ** -0.5
+        self.inv_freq, self.rope_mag = rope_inv_freq(cfg.qk_rope_head_dim, cfg.rope_theta, cfg.rope_scaling)
+        if cfg.rope_scaling:
+            # models/deepseek_v2.py:504-509: softmax scale x mscale(factor, mscale_all_dim)^2
+            m = _yarn_get_mscale(float(cfg.rope_scaling["factor"]), float(cfg.rope_scaling.get("mscale_all_dim", 0)))
+            self.scaling = self.scaling * m * m
 
     # ---- attention ----
     def _attention(self, i, h, positions, req_pool_indices, seq_lens, prefix_lens, extend_lens, loc, force_absorb):
@@ -90,8 +127,8 @@ class DeepseekOracle:
         q_nope, q_pe = q.split([Dn, Dr], dim=-1)
         latent = F.linear(h, w[p + "kv_a_proj_with_mqa.weight"])       # [T, R + Dr]
         c_kv = _rms(latent[:, :R], w[p + "kv_a_layernorm.weight"], cfg.rms_norm_eps)
-        k_pe = _rope_interleaved(latent[:, None, R:], positions, cfg.rope_theta)  # [T, 1, Dr]
-        q_pe = _rope_interleaved(q_pe, positions, cfg.rope_theta)
+        k_pe = _rope_interleaved(latent[:, None, R:], positions, self.inv_freq, self.rope_mag)  # [T, 1, Dr]
+        q_pe = _rope_interleaved(q_pe, positions, self.inv_freq, self.rope_mag)
         # the pool row (both paths write the same thing): [normed c_kv || roped k_pe]
         self.kv[i][loc] = torch.cat([c_kv[:, None, :], k_pe], dim=-1)
         wkv = w[p + "kv_b_proj.weight"].view(H, Dn + Dv, R)
