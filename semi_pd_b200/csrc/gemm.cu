@@ -17,8 +17,11 @@
 //     other contributors dump fp32 partials (coalesced, L2-resident) as their last piece of work
 //     and raise a flag; at the very end the owner adds the partials in ascending-k order to its
 //     parked accumulator and stores C.  Nobody waits before having published its own partial
-//     (no deadlock, all CTAs are co-resident), the wait is short because every CTA has the same
-//     amount of work, and the sum order is fixed (bit-deterministic, no atomics on data).
+//     (no deadlock: the grid never exceeds the caller's SM budget, so all CTAs are co-resident on
+//     a green-context partition; and an owner only ever waits for LOWER-indexed CTAs, which the
+//     block scheduler dispatches first, so even on SMs shared with another kernel the CTAs it
+//     waits for are running or done), the wait is short because every CTA has the same amount of
+//     work, and the sum order is fixed (bit-deterministic, no atomics on data).
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
 // warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global).
