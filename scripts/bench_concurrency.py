@@ -24,8 +24,9 @@ cfg = get_model_config("llama-3-8b")
 CTX, NREQ, EXT = 1088, 8, 1024
 total = ops.device_sm_count(0)
 if kind == "green":
-    p_sms = max(8, int(round(total * pct / 100.0 / 8.0)) * 8)
-    part = ops.SmPartition(0, p_sms, total - p_sms)
+    from semi_pd_b200.semi_pd_scheduler import split_sms
+    p_sms, d_sms0 = split_sms(total, pct, 100 - pct)  # the engine's own split (50 -> 76 + 72)
+    part = ops.SmPartition(0, p_sms, d_sms0)
     p_stream, d_stream, p_sms, d_sms = part.prefill_stream, part.decode_stream, part.prefill_sms, part.decode_sms
 else:
     p_stream, d_stream, p_sms, d_sms = torch.cuda.Stream(), torch.cuda.Stream(priority=-1), 0, 0

@@ -20,8 +20,9 @@ cfg = get_model_config("llama-3-8b")
 cfg.num_hidden_layers = 2
 total = ops.device_sm_count(0)
 if pct < 100:
-    p_sms = max(8, int(round(total * pct / 100.0 / 8.0)) * 8)
-    part = ops.SmPartition(0, p_sms, total - p_sms)
+    from semi_pd_b200.semi_pd_scheduler import split_sms
+    p_sms, d_sms0 = split_sms(total, pct, 100 - pct)  # the engine's own split (50 -> 76 + 72)
+    part = ops.SmPartition(0, p_sms, d_sms0)
     stream, budget = part.prefill_stream, part.prefill_sms
 else:
     stream, budget = torch.cuda.Stream(), 0
