@@ -101,6 +101,14 @@ int spd_gather_rows(void* out, const void* table, const int64_t* idx, int64_t n,
  * Sampler.forward (S/layers/sampler.py:73-77,171).  logits fp32 [B, V] with row stride ld. */
 int spd_argmax_f32(int32_t* ids, const float* logits, int64_t batch, int64_t vocab, int64_t ld,
                    spd_stream_t stream);
+/* Greedy sampling over a vocab-SHARDED lm_head (ParallelLMHead, S/layers/vocab_parallel_embedding.py
+ * + the all-gather of S/layers/logits_processor.py:426-427) without moving the logits:
+ * spd_argmax_partial_f32 writes one 16-byte row per request {f32 max, i32 index_offset + argmax,
+ * 0, 0} for this rank's [B, vocab] shard; after an all-gather of those rows ([parts][B] rows),
+ * spd_argmax_merge picks the winner (ties -> smallest index == torch.argmax of the full row). */
+int spd_argmax_partial_f32(void* pairs, const float* logits, int64_t batch, int64_t vocab, int64_t ld,
+                           int64_t index_offset, spd_stream_t stream);
+int spd_argmax_merge(int32_t* ids, const void* pairs, int parts, int64_t batch, spd_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * batch metadata (integer work; bit-exact)
@@ -212,6 +220,48 @@ int spd_attn_decode_simt(void* out, const void* q, const void* k_pool, const voi
                          int head_dim, int64_t q_stride, int64_t out_stride,
                          int64_t req_to_token_stride, float sm_scale, int dtype, void* workspace,
                          int64_t workspace_bytes, spd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * tensor-parallel all-reduce over NVLink peer memory (one process per GPU) — the `spd_allreduce`
+ * of SURVEY §8b's export list.  Replaces the custom all-reduce the reference sends every
+ * RowParallelLinear output below 8 MiB through (S/layers/linear.py:1265-1266 →
+ * S/distributed/parallel_state.py:376-436 → device_communicators/custom_all_reduce.py:147-160,
+ * 447-480; alternative K/csrc/allreduce/trt_reduce_internal.cu:190-300); larger messages (prefill
+ * batches) go to ncclAllReduce as in parallel_state.py:431-436.
+ *
+ * spd_comm_create allocates this rank's symmetric buffer (3 x max_message_bytes + 8 KB) on the
+ * current device and writes its 64-byte cudaIpcMemHandle to ipc_handle_out; the caller gathers
+ * all ranks' handles (rank order) with any host-side transport and passes them to
+ * spd_comm_connect, which maps the peers (cudaIpcOpenMemHandle).  One communicator belongs to
+ * ONE stream: the prefill and the decode worker of a GPU each create their own, like the
+ * reference's separate NCCL worlds for P and D (S/managers/scheduler.py:250-259).
+ *
+ * spd_allreduce: out[i] = sum over ranks of in[i], i < count (16-bit elements, count % 8 == 0,
+ * count*2 <= max_message_bytes), fp32 accumulation in rank order — bit-identical on all ranks.
+ * `in` and `out` are ordinary device buffers (out may alias in).  All ranks must issue the same
+ * sequence of calls (same counts) on a communicator.  The call is stream-ordered, allocation- and
+ * sync-free and may be captured into a CUDA graph and replayed any number of times (the barrier
+ * sequence numbers live in device memory).  algo: 0 = auto (the reference's dispatch: one-shot
+ * below 512 KB for <= 4 ranks / 256 KB for 8 ranks, two-shot above), 1 = one-shot, 2 = two-shot.
+ * A peer that does not arrive within SPD_AR_TIMEOUT_MS (default 10000) sets a sticky error that
+ * spd_comm_status reports; the GPU never hangs.
+ * ------------------------------------------------------------------------------------------- */
+#define SPD_IPC_HANDLE_BYTES 64
+typedef struct spd_comm spd_comm_t;
+int spd_comm_create(int rank, int world, int64_t max_message_bytes, spd_comm_t** out,
+                    void* ipc_handle_out);
+int spd_comm_connect(spd_comm_t* comm, const void* all_handles);
+int64_t spd_comm_max_bytes(const spd_comm_t* comm);
+int spd_comm_status(spd_comm_t* comm, int* timed_out);
+int spd_allreduce(spd_comm_t* comm, void* out, const void* in, int64_t count, int dtype, int algo,
+                  spd_stream_t stream);
+/* out[r * bytes_per_rank + i] = rank r's in[i] (bytes_per_rank % 16 == 0, <= max_message_bytes):
+ * the all-gather after the vocab-sharded lm_head (S/layers/logits_processor.py:426-427), here of
+ * the per-shard (max, argmax) rows below — and of small logits blocks.  Same ordering /
+ * graph-capture rules as spd_allreduce. */
+int spd_allgather(spd_comm_t* comm, void* out, const void* in, int64_t bytes_per_rank,
+                  spd_stream_t stream);
+int spd_comm_destroy(spd_comm_t* comm);
 
 #ifdef __cplusplus
 }

@@ -292,17 +292,28 @@ class OracleBatch:
     extend_seq_lens: Optional[List[int]] = None
 
 
+class _UpcastOnRead(dict):
+    """16-bit weights that are widened to fp32 each time they are read: same arithmetic as
+    compute="fp32" without holding a second, twice as large copy of an 8B-parameter model."""
+
+    def __getitem__(self, k):
+        return dict.__getitem__(self, k).float()
+
+
 class LlamaOracle:
     """models/llama.py:58-409 + layers/logits_processor.py:244-262,416-442 + layers/sampler.py:73-75,
     over a token-granular KV pool with slot 0 reserved (mem_cache/memory_pool.py:231-250)."""
 
     def __init__(self, cfg, weights: Dict[str, torch.Tensor], kv_slots: int, max_reqs: int,
                  max_ctx: int, compute: str = "native"):
-        assert compute in ("native", "fp32")
+        assert compute in ("native", "fp32", "fp32_lazy")
         self.cfg, self.compute = cfg, compute
         self.dtype = weights["lm_head.weight"].dtype
-        self.w = {k: (v.float() if compute == "fp32" else v) for k, v in weights.items()}
-        self.act_dtype = torch.float32 if compute == "fp32" else self.dtype
+        if compute == "fp32_lazy":
+            self.w = _UpcastOnRead(weights)
+        else:
+            self.w = {k: (v.float() if compute == "fp32" else v) for k, v in weights.items()}
+        self.act_dtype = self.dtype if compute == "native" else torch.float32
         L, Hk, D = cfg.num_hidden_layers, cfg.num_key_value_heads, cfg.head_dim
         self.k_cache = [torch.zeros(kv_slots + 1, Hk, D, dtype=self.act_dtype) for _ in range(L)]
         self.v_cache = [torch.zeros(kv_slots + 1, Hk, D, dtype=self.act_dtype) for _ in range(L)]

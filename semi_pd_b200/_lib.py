@@ -66,6 +66,15 @@ SIGNATURES = {
         _i,
         [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i64, _i64, _i64, _f, _i, _p, _i64, _i, _p],
     ),
+    "spd_comm_create": (_i, [_i, _i, _i64, C.POINTER(_p), _p]),
+    "spd_comm_connect": (_i, [_p, _p]),
+    "spd_comm_max_bytes": (_i64, [_p]),
+    "spd_comm_status": (_i, [_p, C.POINTER(_i)]),
+    "spd_allreduce": (_i, [_p, _p, _p, _i64, _i, _i, _p]),
+    "spd_allgather": (_i, [_p, _p, _p, _i64, _p]),
+    "spd_comm_destroy": (_i, [_p]),
+    "spd_argmax_partial_f32": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p]),
+    "spd_argmax_merge": (_i, [_p, _p, _i, _i64, _p]),
     "spd_attn_prefill_simt": (
         _i,
         [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i, _i, _i64, _i64, _i64, _f, _i, _p],

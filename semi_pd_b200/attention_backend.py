@@ -102,22 +102,22 @@ class SpdAttnBackend(AttentionBackend):
         # cross-checks and serves the head_dim-64 plumbing model (OPT-125m, BASELINE configs[0])
         self.impl = os.environ.get("SPD_ATTN_IMPL", "tc" if self.head_dim == 128 else "simt")
         self.max_extend_len = 0
-        self.decode_workspace = None
-
-    def _workspace(self, bs: int):
-        need = ops.lib.spd_attn_decode_workspace_bytes(bs, self.num_q_heads, self.head_dim)
-        if self.decode_workspace is None or self.decode_workspace.numel() < need:
-            self.decode_workspace = torch.zeros((need,), dtype=torch.uint8, device=self.device)
-        return self.decode_workspace
+        # Split-KV scratch of the decode kernel.  Captured CUDA graphs bake its address in, so it
+        # is allocated exactly ONCE here and never replaced: the kernel only splits when
+        # batch x kv_heads is below the SM count, i.e. for at most ceil(SMs / kv_heads) requests,
+        # which bounds the scratch whatever batch size an eager step later runs with.
+        num_kv_heads = model_runner.model_config.get_num_kv_heads(model_runner.tp_size)
+        sms = ops.device_sm_count(self.device.index or 0)
+        self.split_rows = -(-sms // max(num_kv_heads, 1)) + 1
+        need = ops.lib.spd_attn_decode_workspace_bytes(self.split_rows, self.num_q_heads, self.head_dim)
+        self.decode_workspace = torch.zeros((need,), dtype=torch.uint8, device=self.device)
 
     def init_forward_metadata(self, forward_batch: ForwardBatch):
         if forward_batch.forward_mode.is_extend():
             self.max_extend_len = max(forward_batch.extend_seq_lens_cpu)
-        elif forward_batch.forward_mode.is_decode():
-            self._workspace(forward_batch.batch_size)
 
     def init_cuda_graph_state(self, max_bs: int):
-        self._workspace(max_bs)
+        pass  # the one workspace exists since __init__ and is never reallocated
 
     def init_forward_metadata_capture_cuda_graph(self, bs, num_tokens, req_pool_indices, seq_lens,
                                                  encoder_lens, forward_mode, spec_info=None):

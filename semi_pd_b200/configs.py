@@ -44,6 +44,8 @@ class ModelConfig:
     # "llama" (models/llama.py) or "opt" (BASELINE configs[0]: pre-LN, learned positions, ReLU, biases)
     model_type: str = "llama"
     layer_norm_eps: float = 1e-5
+    # hf_eos_token_id of the reference's ModelConfig (honoured when a request sets ignore_eos=False)
+    eos_token_ids: Optional[List[int]] = None
 
     @property
     def context_len(self) -> int:
@@ -55,7 +57,7 @@ class ModelConfig:
 
 
 _PRESETS = {
-    "llama-3-8b": dict(),
+    "llama-3-8b": dict(eos_token_ids=[128001, 128009]),
     "llama-3.1-8b": dict(
         rope_scaling=dict(rope_type="llama3", factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0,
                           original_max_position_embeddings=8192),
@@ -109,6 +111,7 @@ class ServerArgs:
     attention_backend: str = "spd"
     random_seed: int = 1234
     schedule_conservativeness: float = 1.0
+    allow_auto_truncate: bool = False
     host: str = "127.0.0.1"
     port: int = 30000
     device: str = "cuda"
@@ -134,6 +137,7 @@ class ServerArgs:
         parser.add_argument("--disable-cuda-graph", action="store_true")
         parser.add_argument("--cuda-graph-max-bs", type=int, default=ServerArgs.cuda_graph_max_bs)
         parser.add_argument("--random-seed", type=int, default=ServerArgs.random_seed)
+        parser.add_argument("--allow-auto-truncate", action="store_true")
         parser.add_argument("--host", type=str, default=ServerArgs.host)
         parser.add_argument("--port", type=int, default=ServerArgs.port)
 

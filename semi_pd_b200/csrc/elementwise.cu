@@ -297,7 +297,8 @@ gather_rows_kernel(T* __restrict__ out, const T* __restrict__ table, const int64
 // first maximal element for distinct-valued logits; exact ties are measure-zero on this path).
 constexpr int kArgmaxThreads = 1024;
 __global__ void __launch_bounds__(kArgmaxThreads)
-argmax_kernel(int32_t* __restrict__ ids, const float* __restrict__ logits, int64_t vocab, int64_t ld) {
+argmax_kernel(int32_t* __restrict__ ids, const float* __restrict__ logits, int64_t vocab, int64_t ld,
+              int4* __restrict__ pairs, int idx_offset) {
   __shared__ float sv[32];
   __shared__ int si[32];
   griddep_wait();
@@ -336,9 +337,31 @@ argmax_kernel(int32_t* __restrict__ ids, const float* __restrict__ logits, int64
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
-    if (threadIdx.x == 0) ids[blockIdx.x] = (bi == 0x7fffffff) ? 0 : bi;
+    if (threadIdx.x == 0) {
+      bi = (bi == 0x7fffffff) ? 0 : bi;
+      if (ids) ids[blockIdx.x] = bi;
+      // vocab-sharded lm_head: (max, global index) of this rank's shard, one 16-byte row
+      if (pairs) pairs[blockIdx.x] = make_int4(__float_as_int(best), bi + idx_offset, 0, 0);
+    }
   }
   griddep_launch_dependents();
+}
+
+// ids[b] = index of the largest of `parts` (max, index) candidates per row; ties resolve to the
+// smallest index, so the result equals torch.argmax over the concatenated shards.
+__global__ void argmax_merge_kernel(int32_t* __restrict__ ids, const int4* __restrict__ pairs, int parts,
+                                    int64_t batch) {
+  griddep_wait();
+  const int64_t b = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (b >= batch) return;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int r = 0; r < parts; ++r) {
+    const int4 c = pairs[r * batch + b];
+    const float v = __int_as_float(c.x);
+    if (v > best || (v == best && c.y < bi)) { best = v; bi = c.y; }
+  }
+  ids[b] = (bi == 0x7fffffff) ? 0 : bi;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -665,7 +688,30 @@ int spd_argmax_f32(int32_t* ids, const float* logits, int64_t batch, int64_t voc
               "spd_argmax_f32: bad sizes");
   if (batch == 0) return 0;
   SPD_CUDA(launch(argmax_kernel, dim3((unsigned)batch), dim3(kArgmaxThreads), 0, as_stream(stream),
-                  pdl_enabled(), ids, logits, vocab, ld));
+                  pdl_enabled(), ids, logits, vocab, ld, static_cast<int4*>(nullptr), 0));
+  return 0;
+}
+
+int spd_argmax_partial_f32(void* pairs, const float* logits, int64_t batch, int64_t vocab, int64_t ld,
+                           int64_t index_offset, spd_stream_t stream) {
+  SPD_REQUIRE(pairs && logits, SPD_E_BADARG, "spd_argmax_partial_f32: null pointer");
+  SPD_REQUIRE(aligned16(pairs), SPD_E_ALIGN, "spd_argmax_partial_f32: pairs must be 16-byte aligned");
+  SPD_REQUIRE(batch >= 0 && vocab > 0 && ld >= vocab && index_offset >= 0 &&
+                  index_offset + vocab < 0x7fffffff, SPD_E_BADARG, "spd_argmax_partial_f32: bad sizes");
+  if (batch == 0) return 0;
+  SPD_CUDA(launch(argmax_kernel, dim3((unsigned)batch), dim3(kArgmaxThreads), 0, as_stream(stream),
+                  pdl_enabled(), static_cast<int32_t*>(nullptr), logits, vocab, ld,
+                  static_cast<int4*>(pairs), static_cast<int>(index_offset)));
+  return 0;
+}
+
+int spd_argmax_merge(int32_t* ids, const void* pairs, int parts, int64_t batch, spd_stream_t stream) {
+  SPD_REQUIRE(ids && pairs, SPD_E_BADARG, "spd_argmax_merge: null pointer");
+  SPD_REQUIRE(aligned16(pairs), SPD_E_ALIGN, "spd_argmax_merge: pairs must be 16-byte aligned");
+  SPD_REQUIRE(parts > 0 && batch >= 0, SPD_E_BADARG, "spd_argmax_merge: bad sizes");
+  if (batch == 0) return 0;
+  SPD_CUDA(launch(argmax_merge_kernel, dim3((unsigned)((batch + 127) / 128)), dim3(128), 0,
+                  as_stream(stream), pdl_enabled(), ids, static_cast<const int4*>(pairs), parts, batch));
   return 0;
 }
 

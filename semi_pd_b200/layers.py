@@ -11,8 +11,9 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import ops
-from .distributed import (get_tensor_model_parallel_rank, get_tensor_model_parallel_world_size,
-                          tensor_model_parallel_all_gather, tensor_model_parallel_all_reduce)
+from .distributed import (get_current_comm, get_tensor_model_parallel_rank,
+                          get_tensor_model_parallel_world_size, tensor_model_parallel_all_gather,
+                          tensor_model_parallel_all_reduce)
 from .forward_batch_info import ForwardBatch, LogitsProcessorOutput
 
 
@@ -176,12 +177,13 @@ class RowParallelLinear(LinearBase):
         tp = get_tensor_model_parallel_world_size()
         super().__init__(input_size // tp, output_size)
         self.reduce_results = reduce_results
-        self.tp_group = None  # worker-specific communicator (set by ModelRunner)
 
     def forward(self, x: torch.Tensor):
         out = ops.linear(x, self.weight)
         if self.reduce_results and get_tensor_model_parallel_world_size() > 1:
-            out = tensor_model_parallel_all_reduce(out, self.tp_group)
+            # the calling worker's communicator (distributed.set_current_comm): spd_allreduce for
+            # messages up to 8 MiB, ncclAllReduce above
+            out = tensor_model_parallel_all_reduce(out)
         return out, None
 
     __call__ = forward
@@ -218,12 +220,18 @@ class ParallelLMHead(VocabParallelEmbedding):
 
 class LogitsProcessor:
     """layers/logits_processor.py:220-330,394-446: last-token gather, lm_head matmul in the weight
-    dtype, [all-gather,] slice to vocab, `.float()` — the last two fused into the GEMM epilogue."""
+    dtype, [all-gather,] slice to vocab, `.float()` — the last two fused into the GEMM epilogue.
+
+    TP > 1 (vocab-sharded lm_head): the greedy ids are derived WITHOUT moving the logits — each
+    rank reduces its [bs, vocab/tp] shard to one (max, argmax) row per request, the 16-byte rows
+    are all-gathered through libspd's peer-memory path (graph-capturable) and merged.  The full
+    [bs, vocab] logits of logits_processor.py:426-427 are additionally gathered (NCCL) whenever
+    the call is not being captured into a CUDA graph; a captured decode step returns only this
+    rank's shard in `next_token_logits` (the scheduler consumes ids)."""
 
     def __init__(self, config):
         self.config = config
         self.do_tensor_parallel_all_gather = get_tensor_model_parallel_world_size() > 1
-        self.tp_group = None
 
     def forward(self, input_ids, hidden_states, lm_head, forward_batch: ForwardBatch
                 ) -> LogitsProcessorOutput:
@@ -234,10 +242,17 @@ class LogitsProcessor:
             last_index = forward_batch.extend_start_loc.long() + forward_batch.extend_seq_lens.long() - 1
             pruned_states = ops.gather_rows(hidden_states, last_index)
         logits = ops.linear(pruned_states, lm_head.weight, out_f32=True)
+        next_ids = None
         if self.do_tensor_parallel_all_gather:
-            logits = tensor_model_parallel_all_gather(logits, group=self.tp_group)
+            comm = get_current_comm()
+            shard = logits.shape[1]
+            valid = min(shard, max(self.config.vocab_size - get_tensor_model_parallel_rank() * shard, 1))
+            pairs = ops.argmax_partial(logits[:, :valid], get_tensor_model_parallel_rank() * shard)
+            next_ids = ops.argmax_merge(comm.all_gather_rows16(pairs))
+            if not torch.cuda.is_current_stream_capturing():
+                logits = tensor_model_parallel_all_gather(logits)
         logits = logits[:, : self.config.vocab_size]
-        return LogitsProcessorOutput(next_token_logits=logits)
+        return LogitsProcessorOutput(next_token_logits=logits, next_token_ids=next_ids)
 
     __call__ = forward
 

@@ -22,7 +22,7 @@ from . import ops
 from ._lib import _Counter
 from .attention_backend import SpdAttnBackend
 from .configs import InstanceRole, ModelConfig, ServerArgs, default_cuda_graph_bs
-from .distributed import init_distributed_environment, new_tp_group
+from .distributed import TpComm, init_distributed_environment, set_current_comm
 from .forward_batch_info import ForwardBatch, ForwardMode, LogitsProcessorOutput
 from .layers import Sampler
 from .llama import LlamaForCausalLM
@@ -73,8 +73,11 @@ class ModelRunner:
 
         torch.cuda.set_device(self.device)
         init_distributed_environment(tp_size, tp_rank, device_id=gpu_id)
-        # the prefill worker gets its own communicator (see distributed.new_tp_group)
-        self.tp_group = new_tp_group() if (tp_size > 1 and instance_role == InstanceRole.PREFILL) else None
+        # every worker (the prefill and the decode worker of a GPU alike) owns its communicator —
+        # the reference builds separate NCCL worlds for P and D (managers/scheduler.py:250-259);
+        # it is installed as the calling thread's current communicator before each forward
+        self.tp_comm = TpComm(self.device) if tp_size > 1 else None
+        self.tp_group = self.tp_comm.group if self.tp_comm is not None else None
 
         if not bypass_load_weight:
             self.load_model()
@@ -156,10 +159,10 @@ class ModelRunner:
         self.cuda_graph_runner = None
         if self.server_args.disable_cuda_graph:
             return
-        if self.tp_size > 1:
-            # torch.distributed's NCCL all-reduce captured inside the decode graph hung on the
-            # pool (round 1): TP decode runs eagerly until the graph-safe collective lands
-            logger.warning("TP > 1: decode CUDA graphs disabled")
+        if self.tp_size > 1 and (self.tp_comm is None or self.tp_comm.max_bytes == 0):
+            # only libspd's peer-memory collectives are captured (torch.distributed's NCCL
+            # all-reduce inside the decode graph hung on the pool in round 1)
+            logger.warning("TP > 1 without the libspd communicator: decode CUDA graphs disabled")
             return
         self.cuda_graph_runner = CudaGraphRunner(self)
 
@@ -182,6 +185,7 @@ class ModelRunner:
 
     def forward(self, forward_batch: ForwardBatch, skip_attn_backend_init: bool = False
                 ) -> LogitsProcessorOutput:
+        set_current_comm(self.tp_comm)
         if (forward_batch.forward_mode.is_cuda_graph() and self.cuda_graph_runner
                 and self.cuda_graph_runner.can_run(forward_batch)):
             return self.cuda_graph_runner.replay(forward_batch,
@@ -230,6 +234,7 @@ class CudaGraphRunner:
         return forward_batch.forward_mode.is_decode() and forward_batch.batch_size <= self.max_bs
 
     def capture(self):
+        set_current_comm(self.model_runner.tp_comm)
         stream = torch.cuda.current_stream()
         for bs in reversed(self.capture_bs):
             graph, out = self.capture_one_batch_size(bs, stream)
@@ -251,7 +256,7 @@ class CudaGraphRunner:
             # positions are derived inside the graph from the static seq_lens buffer
             ops.clamp_position(self.seq_lens[:bs], out=self.positions[:bs])
             out = mr.model.forward(fb.input_ids, fb.positions, fb)
-            ids = mr.sampler(out)
+            ids = out.next_token_ids if out.next_token_ids is not None else mr.sampler(out)
             return out.next_token_logits, ids
 
         for _ in range(2):  # warm up (allocations, tensor-map cache, lazy module loads)

@@ -203,6 +203,27 @@ def argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     return out
 
 
+def argmax_partial(logits: torch.Tensor, index_offset: int) -> torch.Tensor:
+    """[B, 16] uint8 rows {f32 max, i32 index_offset + argmax, 0, 0} of one vocab shard."""
+    _cuda(logits)
+    if logits.dtype != torch.float32 or logits.dim() != 2 or logits.stride(1) != 1:
+        raise RuntimeError("argmax_partial: logits must be fp32 [B, V] with a contiguous last dimension")
+    out = torch.empty((logits.shape[0], 16), device=logits.device, dtype=torch.uint8)
+    check(lib.spd_argmax_partial_f32(out.data_ptr(), logits.data_ptr(), logits.shape[0], logits.shape[1],
+                                     logits.stride(0), int(index_offset), _stream()),
+          "spd_argmax_partial_f32")
+    return out
+
+
+def argmax_merge(pairs: torch.Tensor) -> torch.Tensor:
+    """pairs [parts, B, 16] uint8 (argmax_partial rows of every shard) → ids [B] int32."""
+    _cuda(pairs)
+    parts, B = pairs.shape[0], pairs.shape[1]
+    out = torch.empty((B,), device=pairs.device, dtype=torch.int32)
+    check(lib.spd_argmax_merge(out.data_ptr(), pairs.data_ptr(), parts, B, _stream()), "spd_argmax_merge")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # metadata
 # ------------------------------------------------------------------------------------------------

@@ -52,6 +52,11 @@ class Req:
         self.first_token_time: Optional[float] = None
         self.finish_time: Optional[float] = None
         self.token_times: List[float] = []
+        # output / timestamps produced before a retraction (this Req then continues the request
+        # with prompt + those tokens as its input; stitched back together when it finishes)
+        self.prior_output_ids: List[int] = []
+        self.prior_token_times: List[float] = []
+        self.retracted_from: Optional["Req"] = None
 
     @property
     def seqlen(self):
@@ -99,6 +104,7 @@ class ScheduleBatch:
         self.out_cache_loc = None
         self.output_ids = None
         self.seq_lens_sum = 0
+        self.seq_lens_host: List[int] = []   # host mirror of `seq_lens` (the run allocator's view)
         self.prefix_lens = None
         self.extend_lens = None
         self.extend_num_tokens = None
@@ -123,13 +129,10 @@ class ScheduleBatch:
                                "`--max-running-requests`.")
         return idx
 
-    def alloc_token_slots(self, num_tokens: int):
-        out = self.token_to_kv_pool_allocator.alloc(num_tokens)
-        if out is None:
-            raise RuntimeError(f"Prefill out of memory. Try to lower your batch size. "
-                               f"Try to allocate {num_tokens} tokens; available "
-                               f"{self.token_to_kv_pool_allocator.available_size()}.")
-        return out
+    def _oom(self, phase: str, num_tokens: int):
+        return RuntimeError(f"{phase} out of memory. Try to lower your batch size. "
+                            f"Try to allocate {num_tokens} tokens; available "
+                            f"{self.token_to_kv_pool_allocator.available_size()}.")
 
     def _h2d(self, values, dtype):
         return torch.tensor(values, dtype=dtype, pin_memory=True).to(self.device, non_blocking=True)
@@ -172,7 +175,12 @@ class ScheduleBatch:
         extend_lens_t = self._h2d(extend_lens, torch.int64)
 
         if pre_allocated_req_pool_indices is None:
-            self.out_cache_loc = self.alloc_token_slots(extend_num_tokens)
+            # runs: positions [pre, seq) of every request continue its last run, then take whole
+            # new runs (memory_pool.TokenToKVPoolAllocator.alloc_extend)
+            self.out_cache_loc = self.token_to_kv_pool_allocator.alloc_extend(
+                req_pool_indices, prefix_lens, seq_lens)
+            if self.out_cache_loc is None:
+                raise self._oom("Prefill", extend_num_tokens)
             ops.write_req_to_token_pool(self.req_to_token_pool.req_to_token, self.req_pool_indices,
                                         prefix_lens_t, self.seq_lens, extend_lens_t,
                                         self.out_cache_loc)
@@ -185,13 +193,16 @@ class ScheduleBatch:
             self.out_cache_loc = loc32.long()
 
         self.seq_lens_sum = sum(seq_lens)
+        self.seq_lens_host = list(seq_lens)
         self.extend_num_tokens = extend_num_tokens
         self.prefix_lens = prefix_lens
         self.extend_lens = extend_lens
 
     # --- decode ---------------------------------------------------------------------------------
     def check_decode_mem(self, buf_multiplier: int = 1) -> bool:
-        return self.token_to_kv_pool_allocator.available_size() >= len(self.reqs) * buf_multiplier
+        """Can every request of the batch get the slot of its next token?  Exact under the run
+        allocator: only requests whose last run is full need a new one."""
+        return self.token_to_kv_pool_allocator.can_alloc_decode(self.seq_lens_host)
 
     def retract_decode(self, retract_decode_steps: int = 20):
         """Retract requests with the fewest generated tokens / longest prompts first until
@@ -200,13 +211,13 @@ class ScheduleBatch:
                        key=lambda i: (len(self.reqs[i].output_ids), -len(self.reqs[i].origin_input_ids)),
                        reverse=True)
         retracted = []
-        while (self.token_to_kv_pool_allocator.available_size() < len(order) * retract_decode_steps
+        alloc = self.token_to_kv_pool_allocator
+        while (alloc.available_size() < alloc.ceil_to_run(len(order) * retract_decode_steps)
                and len(order) > 1):
             idx = order.pop()
             req = self.reqs[idx]
             retracted.append(req)
-            slots = self.req_to_token_pool.req_to_token[req.req_pool_idx, : req.seqlen - 1]
-            self.token_to_kv_pool_allocator.free(slots.long())
+            alloc.free_req(req.req_pool_idx)
             self.req_to_token_pool.free(req.req_pool_idx)
             req.reset_for_retract()
         self.filter_batch(keep_indices=sorted(order))
@@ -218,12 +229,16 @@ class ScheduleBatch:
         # the token sampled by the previous step is this step's input
         self.input_ids = self.output_ids
         self.output_ids = None
-        self.out_cache_loc = self.alloc_token_slots(bs)
+        self.out_cache_loc = self.token_to_kv_pool_allocator.alloc_decode(
+            [r.req_pool_idx for r in self.reqs], self.seq_lens_host)
+        if self.out_cache_loc is None:
+            raise self._oom("Decode", bs)
         # req_to_token[req, seq_len] = slot ; seq_lens += 1   (schedule_batch.py:1186-1207)
         ops.write_req_to_token_pool(self.req_to_token_pool.req_to_token, self.req_pool_indices,
                                     self.seq_lens, self.seq_lens + 1,
                                     torch.ones_like(self.seq_lens), self.out_cache_loc)
         self.seq_lens = self.seq_lens + 1
+        self.seq_lens_host = [s + 1 for s in self.seq_lens_host]
         self.seq_lens_sum += bs
 
     def filter_batch(self, keep_indices: Optional[List[int]] = None):
@@ -235,14 +250,16 @@ class ScheduleBatch:
             self.reqs = []
             self.req_pool_indices = self.seq_lens = self.output_ids = None
             self.seq_lens_sum = 0
+            self.seq_lens_host = []
             return
         self.reqs = [self.reqs[i] for i in keep_indices]
+        self.seq_lens_host = [self.seq_lens_host[i] for i in keep_indices]
         idx = self._h2d(keep_indices, torch.int64)
         self.req_pool_indices = self.req_pool_indices[idx]
         self.seq_lens = self.seq_lens[idx]
         if self.output_ids is not None:
             self.output_ids = self.output_ids[idx]
-        self.seq_lens_sum = sum(r.seqlen for r in self.reqs)
+        self.seq_lens_sum = sum(self.seq_lens_host)
 
     def merge_batch(self, other: "ScheduleBatch"):
         if self.is_empty():
@@ -250,12 +267,14 @@ class ScheduleBatch:
             self.req_pool_indices, self.seq_lens = other.req_pool_indices, other.seq_lens
             self.output_ids = other.output_ids
             self.seq_lens_sum = other.seq_lens_sum
+            self.seq_lens_host = list(other.seq_lens_host)
             return
         self.req_pool_indices = torch.cat([self.req_pool_indices, other.req_pool_indices])
         self.seq_lens = torch.cat([self.seq_lens, other.seq_lens])
         if self.output_ids is not None and other.output_ids is not None:
             self.output_ids = torch.cat([self.output_ids, other.output_ids])
         self.seq_lens_sum += other.seq_lens_sum
+        self.seq_lens_host = self.seq_lens_host + list(other.seq_lens_host)
         self.reqs.extend(other.reqs)
 
     def get_model_worker_batch(self) -> ModelWorkerBatch:

@@ -23,7 +23,11 @@ class AddReqResult(Enum):
 
 class PrefillAdder:
     def __init__(self, available_size_fn, running_reqs: List[Req], new_token_ratio: float,
-                 rem_input_tokens: int, rem_chunk_tokens: Optional[int]):
+                 rem_input_tokens: int, rem_chunk_tokens: Optional[int], run_len: int = 1):
+        # KV space is handed out in runs of `run_len` slots per request (memory_pool.py), so every
+        # per-request reservation is rounded up to whole runs (the reference's later paged
+        # allocator does the same with its page size)
+        self.run_len = max(int(run_len), 1)
         self.available_size_fn = available_size_fn
         self.new_token_ratio = new_token_ratio
         self.rem_input_tokens = rem_input_tokens
@@ -52,9 +56,12 @@ class PrefillAdder:
             return AddReqResult.OTHER
         return AddReqResult.CONTINUE
 
+    def _ceil(self, tokens: int) -> int:
+        return -(-tokens // self.run_len) * self.run_len
+
     def _prefill_one_req(self, prefix_len: int, extend_input_len: int, max_new_tokens: int):
-        self.rem_total_token_offset += extend_input_len + max_new_tokens
-        self.cur_rem_token_offset += extend_input_len
+        self.rem_total_token_offset += self._ceil(extend_input_len + max_new_tokens)
+        self.cur_rem_token_offset += self._ceil(extend_input_len)
         self.rem_input_tokens -= extend_input_len
         if self.rem_chunk_tokens is not None:
             self.rem_chunk_tokens -= extend_input_len
@@ -72,8 +79,8 @@ class PrefillAdder:
         return req if truncated else None
 
     def add_one_req(self, req: Req, has_chunked_req: bool) -> AddReqResult:
-        total_tokens = req.extend_input_len + min(req.sampling_params.max_new_tokens,
-                                                  CLIP_MAX_NEW_TOKENS_ESTIMATION)
+        total_tokens = self._ceil(req.extend_input_len + min(req.sampling_params.max_new_tokens,
+                                                             CLIP_MAX_NEW_TOKENS_ESTIMATION))
         input_tokens = req.extend_input_len
         prefix_len = len(req.prefix_indices)
         if total_tokens >= self.rem_total_tokens:

@@ -19,6 +19,7 @@ the first token ids.
 from __future__ import annotations
 
 import collections
+import itertools
 import logging
 import queue
 import threading
@@ -27,7 +28,7 @@ from typing import Deque, Dict, List, Optional
 
 import torch
 
-from . import ops
+from . import distributed, ops
 from .configs import (DECODE_ENGINE_SM_PERCENTILE, PREFILL_ENGINE_SM_PERCENTILE, InstanceRole,
                       ModelConfig, ServerArgs, get_model_config)
 from .io_struct import (BatchProcessPrefillResultReq, GetNextPrefillBatchInput,
@@ -62,13 +63,44 @@ class SemiPDScheduler:
         self.stop_flag = threading.Event()
         self.error: Optional[BaseException] = None
         self.forward_ct = 0
+        self.tp_rank = worker.tp_rank
+        self.tp_size = server_args.tp_size
         # bench.py's device-resident arm: prompt ids are sliced from HBM and sampled ids never
         # leave the device (completion is by launch count); off for normal serving
         self.device_resident = False
 
+    def validate_request(self, input_ids: List[int], max_new_tokens: int, strict: bool = True):
+        """managers/utils.py:10-44 (`validate_input_length`) + scheduler.py:791-798: an input that
+        cannot fit the context / the KV pool is rejected (the reference aborts it with
+        BAD_REQUEST unless --allow-auto-truncate), and max_new_tokens is clipped so that
+        prompt + output stay inside `max_req_len` — which also bounds the request's
+        req_to_token row and RoPE positions.  → (input_ids, max_new_tokens)."""
+        w = self.tp_worker
+        n = len(input_ids)
+        if n == 0:
+            if strict:
+                raise ValueError("empty input_ids")
+            input_ids, n = [0], 1
+        if n >= w.max_req_input_len:
+            if strict and not getattr(self.server_args, "allow_auto_truncate", False):
+                raise ValueError(f"Input length ({n} tokens) exceeds the maximum allowed length "
+                                 f"({w.max_req_input_len} tokens). Use a shorter input or enable "
+                                 f"--allow-auto-truncate.")
+            input_ids = input_ids[: w.max_req_input_len]
+            n = len(input_ids)
+        max_new_tokens = min(max_new_tokens if max_new_tokens is not None else 1 << 30,
+                             w.max_req_len - n - 1)
+        return input_ids, max(int(max_new_tokens), 1)
+
     def handle_generate_request(self, recv_req: TokenizedGenerateReqInput):
-        req = Req(recv_req.rid, recv_req.input_ids, recv_req.sampling_params,
-                  arrival_time=recv_req.arrival_time)
+        sp = recv_req.sampling_params
+        if not recv_req.is_retracted:
+            # the engine front (SemiPDEngine.submit) already rejected what must be rejected; a
+            # scheduler thread never raises on a request, it clips
+            recv_req.input_ids, sp.max_new_tokens = self.validate_request(
+                recv_req.input_ids, sp.max_new_tokens, strict=False)
+        req = Req(recv_req.rid, recv_req.input_ids, sp, arrival_time=recv_req.arrival_time,
+                  eos_token_ids=set(getattr(self.tp_worker.model_config, "eos_token_ids", None) or ()))
         req.input_ids_device = recv_req.input_ids_device
         if recv_req.is_retracted:
             self.waiting_queue.insert(0, req)  # semi_pd_scheduler.py:52-56
@@ -79,6 +111,7 @@ class SemiPDScheduler:
     def _thread_setup(self):
         torch.cuda.set_device(self.device)
         ops.set_sm_budget(self.sm_budget)
+        distributed.set_current_comm(self.tp_worker.model_runner.tp_comm)
 
     def run(self):
         try:
@@ -101,9 +134,14 @@ class SemiPDPrefillScheduler(SemiPDScheduler):
         self.chunked_rid: Optional[str] = None
         self.prefill_tokens = 0
         self.prefill_busy_s = 0.0
-        n_ids = max(int(server_args.max_running_requests or 256), 256)
+        # sized by the admission limit the decode side actually enforces (a prefill batch may hold
+        # as many short prompts as max_running_requests allows); grown on demand beyond that
+        n_ids = max(int(getattr(worker, "max_running_requests", 0) or 0), 256)
         self._pinned_ids = [torch.empty(n_ids, dtype=torch.int32).pin_memory()
                             for _ in range(self.MAX_LAUNCHED_BATCHES + 2)]
+        # TP ranks > 0 hand their (identical) result to the local decode scheduler directly; only
+        # rank 0's report travels through D's inbox and is broadcast (scheduler.py:599-659)
+        self.local_result_queue: Optional["queue.Queue"] = None
 
     def recv_requests(self):
         while True:
@@ -176,7 +214,10 @@ class SemiPDPrefillScheduler(SemiPDScheduler):
             ids = next_token_ids.to(torch.int64)  # stays in HBM; D consumes it after done_event
         else:
             # async D2H into pinned memory; read after the event (the only host wait of the worker)
-            ids = self._pinned_ids[self.forward_ct % len(self._pinned_ids)][:n]
+            k = self.forward_ct % len(self._pinned_ids)
+            if n > self._pinned_ids[k].numel():
+                self._pinned_ids[k] = torch.empty(n, dtype=torch.int32).pin_memory()
+            ids = self._pinned_ids[k][:n]
             ids.copy_(next_token_ids[:n], non_blocking=True)
         done = torch.cuda.Event()
         done.record(self.stream)
@@ -190,7 +231,11 @@ class SemiPDPrefillScheduler(SemiPDScheduler):
         if not self.device_resident:
             ids = ids.tolist()
         self.prefill_busy_s += time.perf_counter() - t0
-        self.send_to_d_instance.put(BatchProcessPrefillResultReq(next_token_ids=ids, done_event=done))
+        msg = BatchProcessPrefillResultReq(next_token_ids=ids, done_event=done)
+        if self.tp_size > 1 and self.tp_rank != 0:
+            self.local_result_queue.put(msg)
+        else:
+            self.send_to_d_instance.put(msg)
 
 
 class SemiPDDecodeScheduler(SemiPDScheduler):
@@ -216,26 +261,86 @@ class SemiPDDecodeScheduler(SemiPDScheduler):
         self.new_token_ratio = self.init_new_token_ratio
         self.finished: "queue.Queue[Req]" = queue.Queue()
         self.num_finished = 0
+        self.num_retracted = 0
         self.decode_tokens = 0
         self.decode_steps = 0
         self.result_queue: Deque = collections.deque()
         self._pinned_ring = [torch.empty((4096,), dtype=torch.int32, pin_memory=True) for _ in range(4)]
         self._ring_i = 0
         self.token_callback = None  # optional: fn(req, token_id, finished) — the detokenizer hook
+        # TP > 1: rank 0 broadcasts the messages it drained every iteration so that all ranks'
+        # decode schedulers take identical decisions in lockstep (scheduler.py:599-659)
+        self.cpu_group = None
+        self.local_prefill_results: "queue.Queue" = queue.Queue()
+        self._stop_broadcast = False
 
     # ---- inbound -------------------------------------------------------------------------------
-    def recv_requests(self):
+    def _drain_inbox(self) -> list:
+        msgs = []
         while True:
             try:
-                msg = self.inbox.get_nowait()
+                msgs.append(self.inbox.get_nowait())
             except queue.Empty:
-                return
-            if isinstance(msg, TokenizedGenerateReqInput):
+                return msgs
+
+    def _dispatch(self, msg):
+        if isinstance(msg, TokenizedGenerateReqInput):
+            self.handle_generate_request(msg)
+        elif isinstance(msg, BatchProcessPrefillResultReq):
+            self.process_prefill_result(msg)
+        elif isinstance(msg, GetNextPrefillBatchInput):
+            self.get_next_prefill_batch(msg)
+
+    def recv_requests(self):
+        if self.tp_size == 1:
+            for msg in self._drain_inbox():
+                self._dispatch(msg)
+            return
+        # Lockstep under TP: what rank 0 received this iteration is what every rank processes
+        # this iteration (the reference's broadcast_pyobj over the gloo group).  Device handles
+        # (CUDA events) cannot travel; every rank substitutes its own prefill worker's report.
+        import torch.distributed as dist
+        if self.tp_rank == 0:
+            msgs = self._drain_inbox()
+            wire = []
+            for m in msgs:
+                if isinstance(m, TokenizedGenerateReqInput):
+                    wire.append(("gen", m.rid, m.input_ids, m.sampling_params.max_new_tokens,
+                                 m.sampling_params.ignore_eos, m.arrival_time))
+                elif isinstance(m, BatchProcessPrefillResultReq):
+                    wire.append(("prefill_result",))
+            if self.stop_flag.is_set():
+                wire.append(("stop",))
+            box = [wire]
+            dist.broadcast_object_list(box, src=0, group=self.cpu_group)
+            if self.stop_flag.is_set():
+                self._stop_broadcast = True
+            for m in msgs:
+                self._dispatch(m)
+            return
+        box = [None]
+        dist.broadcast_object_list(box, src=0, group=self.cpu_group)
+        for w in box[0]:
+            if w[0] == "gen":
+                msg = TokenizedGenerateReqInput(
+                    rid=w[1], input_text="", input_ids=list(w[2]),
+                    sampling_params=SamplingParams(max_new_tokens=w[3], ignore_eos=w[4]), arrival_time=w[5])
+                self.send_to_p_instance.put(msg)  # P knows the rid before D can schedule it
                 self.handle_generate_request(msg)
-            elif isinstance(msg, BatchProcessPrefillResultReq):
-                self.process_prefill_result(msg)
-            elif isinstance(msg, GetNextPrefillBatchInput):
-                self.get_next_prefill_batch(msg)
+            elif w[0] == "prefill_result":
+                # this rank's prefill worker ran the same batch; wait for ITS report (its ids are
+                # identical, its done_event orders this rank's KV writes before the decode steps)
+                while True:
+                    try:
+                        local = self.local_prefill_results.get(timeout=0.5)
+                        break
+                    except queue.Empty:
+                        if self.stop_flag.is_set():
+                            return
+                self.process_prefill_result(local)
+            elif w[0] == "stop":
+                self._stop_broadcast = True
+                self.stop_flag.set()
 
     # ---- prefill admission (D decides, P computes) ------------------------------------------------
     def propose_prefill_candidates(self) -> List[str]:
@@ -267,7 +372,8 @@ class SemiPDDecodeScheduler(SemiPDScheduler):
         # slots promised to in-flight prefill batches' future decode growth count as running
         running_reqs = list(self.running_batch.reqs) + [r for b in self.scheduled_prefill_batches for r in b.reqs]
         adder = PrefillAdder(self.token_to_kv_pool_allocator.available_size, running_reqs,
-                             self.new_token_ratio, self.max_prefill_tokens, self.chunked_prefill_size)
+                             self.new_token_ratio, self.max_prefill_tokens, self.chunked_prefill_size,
+                             run_len=self.token_to_kv_pool_allocator.run_len)
         if self.chunked_req is not None:
             self.chunked_req.init_next_round_input(prefix_len=len(self.chunked_req.fill_ids))
             self.chunked_req = adder.add_chunked_req(self.chunked_req)
@@ -327,7 +433,8 @@ class SemiPDDecodeScheduler(SemiPDScheduler):
                 continue  # intermediate chunk: the sampled token is discarded
             req.output_ids.append(int(tok))
             req.launched_tokens = 1
-            req.first_token_time = now
+            if req.first_token_time is None:  # a retracted request keeps its original TTFT
+                req.first_token_time = now
             req.token_times.append(now)
             req.check_finished()
             if self.token_callback:
@@ -352,15 +459,21 @@ class SemiPDDecodeScheduler(SemiPDScheduler):
 
     # ---- decode ----------------------------------------------------------------------------------
     def _release(self, req: Req):
-        """Free the KV slots and the request slot (ChunkCache.cache_finished_req,
-        mem_cache/chunk_cache.py:37-42)."""
-        n = len(req.origin_input_ids) + max(req.launched_tokens - 1, 0)
-        slots = self.req_to_token_pool.req_to_token[req.req_pool_idx, :n]
-        self.token_to_kv_pool_allocator.free(slots.long())
+        """Free the KV runs and the request slot (ChunkCache.cache_finished_req,
+        mem_cache/chunk_cache.py:37-42) and hand the request to the output side."""
+        self.token_to_kv_pool_allocator.free_req(req.req_pool_idx)
         self.req_to_token_pool.free(req.req_pool_idx)
         req.finish_time = time.perf_counter()
+        if req.prior_output_ids:
+            # the request was retracted and re-prefilled on the way: the client sees ONE request
+            # with its whole output, its original first-token time and every token's timestamp
+            req.origin_input_ids = req.origin_input_ids[: len(req.origin_input_ids) - len(req.prior_output_ids)]
+            req.output_ids = req.prior_output_ids + req.output_ids
+            req.token_times = req.prior_token_times + req.token_times
+            req.prior_output_ids, req.prior_token_times = [], []
         self.num_finished += 1
-        self.finished.put(req)
+        if self.tp_rank == 0:
+            self.finished.put(req)
 
     def update_running_batch(self, batch: ScheduleBatch) -> ScheduleBatch:
         # requests whose last token has already been LAUNCHED need no further step
@@ -387,7 +500,12 @@ class SemiPDDecodeScheduler(SemiPDScheduler):
                                                     ignore_eos=req.sampling_params.ignore_eos),
                                                 is_retracted=True, arrival_time=req.arrival_time)
                 new_req = self.handle_generate_request(msg)
+                # history the continuation must report when it finishes (stitched in _release)
                 new_req.retracted_from = req
+                new_req.prior_output_ids = req.prior_output_ids + req.output_ids
+                new_req.prior_token_times = req.prior_token_times + req.token_times
+                new_req.first_token_time = req.first_token_time
+                self.num_retracted += 1
                 self.send_to_p_instance.put(msg)
         else:
             self.new_token_ratio = max(self.new_token_ratio - self.new_token_ratio_decay,
@@ -444,8 +562,12 @@ class SemiPDDecodeScheduler(SemiPDScheduler):
     def event_loop(self):
         """Overlap loop: step N is launched before step N-1's tokens are read back."""
         idle_spins = 0
-        while not self.stop_flag.is_set():
+        # TP > 1: every rank leaves the loop in the SAME iteration — when the "stop" rank 0
+        # broadcast has been processed — or the others would block in the next broadcast
+        while not (self._stop_broadcast if self.tp_size > 1 else self.stop_flag.is_set()):
             self.recv_requests()
+            if self._stop_broadcast:
+                break
             self.maybe_schedule_prefill()
             batch = self.get_next_batch_to_run()
             if batch is not None:
@@ -507,6 +629,11 @@ class SemiPDEngine:
         else:
             raise ValueError(partition)
 
+        self.tp_rank, self.tp_size = tp_rank, server_args.tp_size
+        if self.tp_size > 1:
+            # rendezvous before the workers build their communicators (model_runner.py:285-344)
+            distributed.init_distributed_environment(self.tp_size, tp_rank, device_id=gpu_id)
+
         # D first: owns weights and the KV pool (engine.py:584-627)
         with torch.cuda.stream(self.d_stream):
             ops.set_sm_budget(self.d_sms)
@@ -524,6 +651,7 @@ class SemiPDEngine:
             self.p_worker.share_params_from_ipc(ipc_info)
             self.p_worker.init_attention_backend()
         ops.set_sm_budget(0)
+        distributed.set_current_comm(None)
         self.max_total_num_tokens = self.d_worker.max_total_num_tokens
 
         self.decode = SemiPDDecodeScheduler(server_args, self.d_worker, self.d_stream, self.d_sms)
@@ -531,11 +659,19 @@ class SemiPDEngine:
                                               self.decode.inbox)
         self.decode.send_to_p_instance = self.prefill.inbox
         self.decode.bridge_socket = self.prefill.bridge_socket
+        self.prefill.local_result_queue = self.decode.local_prefill_results
+        if self.tp_size > 1:
+            import datetime
+
+            import torch.distributed as dist
+            self.decode.cpu_group = dist.new_group(ranks=list(range(self.tp_size)), backend="gloo",
+                                                   timeout=datetime.timedelta(seconds=300))
         self.threads = [threading.Thread(target=self.decode.run, name="semi-pd-decode", daemon=True),
                         threading.Thread(target=self.prefill.run, name="semi-pd-prefill", daemon=True)]
         for t in self.threads:
             t.start()
-        self._rid = 0
+        self._rid = itertools.count(1)
+        self._closed = False
 
     def warmup(self, prompt_len: int = 64, n: int = 2, max_new_tokens: int = 4):
         """Run a few requests through both workers (module loads, tensor-map cache, allocator)."""
@@ -551,10 +687,17 @@ class SemiPDEngine:
 
     def submit(self, input_ids: List[int], max_new_tokens: int, arrival_time: Optional[float] = None,
                ignore_eos: bool = True, input_ids_device: Optional[torch.Tensor] = None) -> str:
-        """TokenizerManager.generate_request → push to D and P (tokenizer_manager.py:149-160)."""
-        self._rid += 1
-        rid = f"req-{self._rid}"
-        msg = TokenizedGenerateReqInput(rid=rid, input_text="", input_ids=list(input_ids),
+        """TokenizerManager.generate_request → push to D and P (tokenizer_manager.py:149-160).
+        Raises ValueError for a request the reference would abort with BAD_REQUEST (input longer
+        than the context / KV pool allows); max_new_tokens is clipped like scheduler.py:791-798.
+        Under TP only rank 0 accepts requests (its decode scheduler broadcasts them)."""
+        if self.tp_size > 1 and self.tp_rank != 0:
+            raise RuntimeError("TP > 1: requests are submitted on rank 0 only")
+        if self.tp_size > 1 and (input_ids_device is not None or self.decode.device_resident):
+            raise RuntimeError("the device-resident arm is a TP = 1 measurement mode")
+        input_ids, max_new_tokens = self.decode.validate_request(list(input_ids), max_new_tokens)
+        rid = f"req-{next(self._rid)}"  # itertools.count: atomic under the GIL (FastAPI threadpool)
+        msg = TokenizedGenerateReqInput(rid=rid, input_text="", input_ids=input_ids,
                                         sampling_params=SamplingParams(max_new_tokens=max_new_tokens,
                                                                        ignore_eos=ignore_eos),
                                         arrival_time=time.perf_counter() if arrival_time is None else arrival_time,
@@ -579,11 +722,45 @@ class SemiPDEngine:
             if s.error is not None:
                 raise RuntimeError(f"{s.role} scheduler died") from s.error
 
-    def shutdown(self):
-        self.decode.stop_flag.set()
+    def join(self, timeout: Optional[float] = None):
+        """TP ranks > 0: serve until rank 0's shutdown has been broadcast."""
+        for t in self.threads:
+            t.join(timeout=timeout)
+
+    def shutdown(self, destroy_partition: bool = True):
+        """Stop both loops, drop everything that lives on the partition streams (CUDA graphs, the
+        workers' tensors, cached allocator blocks) and then destroy the green contexts
+        (`spd_partition_destroy`).  Under TP rank 0's call ends the loops of all ranks; the other
+        ranks' calls wait for that."""
+        if self._closed:
+            return
+        self._closed = True
+        if self.tp_size == 1 or self.tp_rank == 0:
+            self.decode.stop_flag.set()
+        for t in self.threads[:1]:
+            t.join(timeout=60)
         self.prefill.stop_flag.set()
+        self.decode.stop_flag.set()
         for t in self.threads:
             t.join(timeout=10)
         torch.cuda.synchronize()
-        # the green contexts are left to process teardown: tensors / events created on their
-        # streams may outlive this call, and destroying the context under them aborts the process
+        for w in (self.d_worker, self.p_worker):
+            mr = w.model_runner
+            mr.cuda_graph_runner = None
+            mr.attn_backend = None
+            if mr.tp_comm is not None:
+                mr.tp_comm.close()
+                mr.tp_comm = None
+        if destroy_partition and self.partition is not None:
+            # nothing may still reference the partition's streams: the graphs are gone, the
+            # threads have exited, the device is idle; cached blocks of the stream-keyed
+            # allocator pools go back to the driver first
+            import gc
+            self.decode = self.prefill = None
+            self.d_worker = self.p_worker = None
+            gc.collect()
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+            self.p_stream = self.d_stream = None
+            self.partition.close()
+            self.partition = None

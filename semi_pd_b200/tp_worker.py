@@ -45,7 +45,10 @@ class TpModelWorker:
         self.max_running_requests = min(
             self.max_total_num_tokens // 2 if self.server_args.max_running_requests is None
             else self.server_args.max_running_requests, mr.req_to_token_pool.size - 1)
-        self.max_req_len = min(self.model_config.context_len - 1, self.max_total_num_tokens - 1)
+        # --context-length overrides the model's (it also sizes the req_to_token rows,
+        # model_runner.py:1039-1045), tp_worker.py:100-107
+        context_len = self.server_args.context_length or self.model_config.context_len
+        self.max_req_len = min(context_len - 1, self.max_total_num_tokens - 1)
         self.max_req_input_len = self.max_req_len - 5
 
     def get_worker_info(self):

@@ -1,7 +1,13 @@
-"""Tensor-parallel forward path on real GPUs (needs >= 2; skipped otherwise): two ranks, NCCL,
-sharded heads / FFN columns, SUM all-reduce after o_proj and down_proj only, vocab-sharded lm_head
-with an all-gather of the logits.  Every rank must reproduce the unsharded CPU
-oracle's logits; decode also runs through the captured CUDA graph (NCCL inside the graph)."""
+"""Tensor-parallel forward path on real GPUs (needs >= 2; skipped otherwise): N ranks, sharded
+heads / FFN columns, SUM all-reduce after o_proj and down_proj only — libspd's peer-memory
+`spd_allreduce` (one-shot / two-shot over IPC-mapped buffers) for decode-sized messages, NCCL above
+8 MiB — and a vocab-sharded lm_head whose greedy ids come from an all-gather of (max, argmax) rows
+(SURVEY §8e).  Every rank must reproduce the unsharded CPU oracle's logits; decode runs both
+eagerly and through the captured CUDA graph (the collective is inside the graph); the semi-PD
+engine runs with tp_size = 2 (P and D on separate communicators, rank 0 broadcasting the decode
+scheduler's messages) and must produce the sequential oracle's tokens.
+The driver's GPUTEST box has one GPU: the pass is recorded by `gpurun --gpus 2` logs under
+profiles/ and by `bench.py --gpus N`'s `tp_parity` block in every SCALE run."""
 import os
 import socket
 
@@ -54,14 +60,41 @@ def _worker(rank, world, port, use_graph, ret):
         lc, _ = os_.decode(rids, tok)
         err = max(err, (lg - lc).abs().max().item())
         tok = lc.argmax(-1).tolist()
+    # the collectives themselves, against NCCL, eager and replayed from a graph
+    comm = mr.tp_comm
+    assert comm is not None and comm.max_bytes > 0, "libspd communicator missing"
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    for n, algo in [(8, 1), (4096 * 3, 1), (4096 * 64, 1), (4096 * 64, 2), (4096 * 160 + 8, 2), (4096 * 512, 0)]:
+        x = torch.randn(n, generator=g, device="cuda", dtype=dtype)
+        ref = x.float().clone()
+        torch.distributed.all_reduce(ref)
+        y = comm.all_reduce(x.clone(), algo=algo)
+        assert (y.float() - ref).abs().max().item() <= 2e-2 * max(ref.abs().max().item(), 1.0), (n, algo)
+        # bit-identical on all ranks
+        z = y.clone()
+        torch.distributed.broadcast(z, src=0)
+        assert torch.equal(z, y), (n, algo)
+    x = torch.randn(4096 * 8, generator=g, device="cuda", dtype=dtype)
+    static_in, ref = x.clone(), x.float().clone()
+    torch.distributed.all_reduce(ref)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        static_out = comm.all_reduce(static_in * 1, algo=0)
+        static_out2 = comm.all_reduce(static_out * 1, algo=1)  # an odd number of calls per replay
+        static_out3 = comm.all_reduce(static_in * 1, algo=2)
+    for _ in range(5):
+        gr.replay()
+    torch.cuda.synchronize()
+    assert (static_out.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    assert torch.equal(static_out3, static_out)
+    assert comm.status() == 0
     ret[rank] = err
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
 
-# NOTE: capturing torch.distributed's NCCL all-reduce inside the decode CUDA graph hung on the pool
-# (round 1); TP decode therefore runs eagerly for now — the graph-safe collective is a §8(f) row.
-@pytest.mark.parametrize("use_graph", [False], ids=["eager"])
+@pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "cuda-graph"])
 def test_tp2_matches_unsharded_oracle(use_graph):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -73,3 +106,79 @@ def test_tp2_matches_unsharded_oracle(use_graph):
         errs = dict(ret)
     assert set(errs) == {0, 1}
     assert max(errs.values()) < 1e-2, errs
+
+
+ECFG = dict(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+            num_key_value_heads=2, head_dim=128, vocab_size=1024, max_position_embeddings=2048)
+
+
+def _engine_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from oracle import llama_oracle as O
+    import semi_pd_b200.model_runner as MR
+    from semi_pd_b200.configs import ModelConfig, ServerArgs
+    from semi_pd_b200.semi_pd_scheduler import SemiPDEngine
+
+    dtype = torch.float16
+    ocfg = O.OracleLlamaConfig(**ECFG)
+    weights = O.make_weights(ocfg, dtype, seed=77)
+    sa = ServerArgs(model_path="tiny", dtype="float16", load_format="external", tp_size=world,
+                    max_total_tokens=8192, max_running_requests=16, context_length=1024, enable_semi_pd=True,
+                    cuda_graph_bs=[1, 2, 4, 8, 16], chunked_prefill_size=96, max_prefill_tokens=4096)
+    orig = MR.ModelRunner.load_model
+
+    def load_with_weights(self):
+        orig(self)
+        self.model.load_weights(weights.items())
+
+    MR.ModelRunner.load_model = load_with_weights
+    eng = SemiPDEngine(sa, gpu_id=rank, tp_rank=rank, model_config=ModelConfig(name="tiny", **ECFG),
+                       prefill_sm_percent=50, decode_sm_percent=50)
+    MR.ModelRunner.load_model = orig
+    lens = [5, 130, 17, 64, 257, 1, 33, 200]
+    n_new = 10
+    prompts = [[(11 + 7 * i + 29 * j) % ECFG["vocab_size"] for i in range(n)] for j, n in enumerate(lens)]
+    if rank == 0:
+        try:
+            assert eng.d_worker.model_runner.cuda_graph_runner is not None, "decode graphs must be on under TP"
+            rids = [eng.submit(p, n_new) for p in prompts]
+            done = {r.rid: r for r in eng.wait(len(prompts), timeout=180)}
+            got = [done[r].output_ids for r in rids]
+        finally:
+            eng.shutdown()
+        bad = 0
+        checked = 0
+        for p, g_ in zip(prompts, got):
+            m = O.LlamaOracle(ocfg, weights, kv_slots=2048, max_reqs=4, max_ctx=1100, compute="fp32")
+            s = O.OracleSession(m, 2048, 4)
+            rids_o, logits, _ = s.extend([p])
+            for k in range(n_new):
+                top2 = logits.topk(2, -1).values[0]
+                if float(top2[0] - top2[1]) <= 2e-2:
+                    break
+                t = int(logits.argmax(-1)[0])
+                bad += int(g_[k] != t)
+                checked += 1
+                if k + 1 < n_new:
+                    logits, _ = s.decode(rids_o, [t])
+        ret["checked"], ret["bad"] = checked, bad
+    else:
+        eng.join()
+        eng.shutdown()
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_tp2_semi_pd_engine_matches_sequential_oracle():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_engine_worker, args=(world, port, ret), nprocs=world, join=True)
+        out = dict(ret)
+    assert out["bad"] == 0 and out["checked"] > 40, out

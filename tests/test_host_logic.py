@@ -22,7 +22,7 @@ def test_forward_mode_values_and_predicates():
     assert ForwardMode.DECODE.is_cuda_graph() and ForwardMode.IDLE.is_decode_or_idle()
 
 
-def test_req_to_token_pool_and_allocator():
+def test_req_to_token_pool():
     pool = ReqToTokenPool(size=5, max_context_len=16, device="cpu")
     assert pool.req_to_token.dtype == torch.int32 and pool.req_to_token.shape == (5, 16)
     a = pool.alloc(3)
@@ -30,19 +30,58 @@ def test_req_to_token_pool_and_allocator():
     pool.free(a[1])
     pool.free([a[0]])
     assert pool.available_size() == 4
-    alloc = TokenToKVPoolAllocator(10, torch.bfloat16, "cpu", kvcache=None)
-    # slot 0 is the dummy slot for padded CUDA-graph rows (memory_pool.py:179-182)
-    assert alloc.free_slots.tolist() == list(range(1, 11)) and alloc.free_slots.dtype == torch.int64
-    s = alloc.alloc(4)
-    assert s.tolist() == [1, 2, 3, 4] and alloc.alloc(7) is None
+    with pytest.raises(RuntimeError):
+        pool.free(a[1])  # double free is an error, not a silently duplicated slot
+    pool.clear()
+    assert pool.available_size() == 5
+
+
+def test_run_allocator_contract_and_runs():
+    """External contract of memory_pool.py:124-184 (page_size 1, int64 slot ids, slot 0 reserved,
+    alloc / free / available_size) over an allocator that hands out runs of consecutive slots."""
+    R = 8
+    alloc = TokenToKVPoolAllocator(50, torch.bfloat16, "cpu", kvcache=None, run_len=R)
+    assert alloc.page_size == 1 and alloc.num_runs == 6 and alloc.available_size() == 48
+    # request-agnostic contract: ids are int64, never 0, consecutive inside a run
+    s = alloc.alloc(11)
+    assert s.dtype == torch.int64 and s.tolist() == list(range(1, 12)) and alloc.available_size() == 32
+    assert alloc.alloc(33) is None and alloc.available_size() == 32
     alloc.free_group_begin()
-    alloc.free(s[:2])
-    alloc.free(s[2:])
-    assert alloc.available_size() == 6
+    alloc.free(s[:3])
+    alloc.free(s[3:8])
+    assert alloc.available_size() == 32     # nothing returns before the group ends
     alloc.free_group_end()
-    assert alloc.available_size() == 10
+    assert alloc.available_size() == 40     # run 0 is whole again; run 1 still holds slots 9..11
+    alloc.free(s[8:])
+    assert alloc.available_size() == 48
+    with pytest.raises(RuntimeError):
+        alloc.free(s[:1])
     alloc.clear()
-    assert alloc.available_size() == 10
+    # request-aware entry points: positions [k*R, k*R + R) of a request are R consecutive slots
+    loc = alloc.alloc_extend([3, 4], [0, 0], [13, 5])
+    a, b = loc[:13].tolist(), loc[13:].tolist()
+    assert a[:8] == list(range(a[0], a[0] + 8)) and a[8:] == list(range(a[8], a[8] + 5))
+    assert (a[0] - 1) % R == 0 and (a[8] - 1) % R == 0 and (b[0] - 1) % R == 0 and 0 not in a + b
+    assert alloc.available_size() == 48 - 3 * R
+    # chunked continuation fills the request's last run before taking a new one
+    loc2 = alloc.alloc_extend([3], [13], [20]).tolist()
+    assert loc2[:3] == [a[12] + 1, a[12] + 2, a[12] + 3] and (loc2[3] - 1) % R == 0
+    assert alloc.req_slots(3).tolist() == a + loc2
+    # decode: one slot per request, continuing its run; a full run takes a new one
+    assert alloc.can_alloc_decode([20, 5])
+    d = alloc.alloc_decode([3, 4], [20, 5]).tolist()
+    assert d == [loc2[-1] + 1, b[-1] + 1]
+    for step in range(21, 24):
+        alloc.alloc_decode([3], [step])
+    assert alloc.available_size() == 48 - 4 * R  # request 3 holds 24 tokens = 3 runs, request 4 one
+    nxt = alloc.alloc_decode([3], [24]).tolist()
+    assert (nxt[0] - 1) % R == 0 and alloc.available_size() == 48 - 5 * R
+    # exhaustion is reported, not half-applied
+    assert alloc.alloc_extend([9], [0], [3 * R]) is None and alloc.available_size() == 8
+    with pytest.raises(RuntimeError):
+        alloc.alloc_extend([3], [7], [9])    # prefix does not match what the request holds
+    assert alloc.free_req(3) == 25 and alloc.free_req(4) == 6 and alloc.available_size() == 48
+    assert alloc.free_req(4) == 0
 
 
 def test_cuda_graph_batch_sizes_and_presets():
