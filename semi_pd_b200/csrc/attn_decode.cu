@@ -23,18 +23,26 @@
 // kept per thread and reduced once per item.  Raising m_ref (always on an item's first tile,
 // rarely afterwards) takes the slow path: true tile max via shuffles, O^T rescaled in TMEM.
 //
-// warps 0-3: softmax, O rescale, epilogue     warps 4-5 / 6-7: K / V gather through req_to_token
-// (16-byte cp.async, 128-byte swizzle; separate 3-slot rings) + Q staging     warp 8: MMA issuer +
-// TMEM allocator.
-// Why cp.async and not TMA: the pool is token-granular, so a tile is 128 scattered 256-byte rows.
-// tile::gather4 (4 rows x 128 B per instruction) was built and measured on B200: correct (the
-// swizzle and the zero fill of out-of-range rows match, scripts/probes/gather4_probe.cu) but the
-// TMA unit retires only ~1 such instruction per 27 clk -> 36 GB/s per SM against 47 GB/s for this
-// cp.async gather (profiles/r01_decode_attention_loader_experiments.md).
+// warps 0-3: softmax, O rescale, epilogue     warps 4-5 / 6-7: K / V loaders (separate 3-slot
+// rings) + Q staging     warp 8: MMA issuer + TMEM allocator.
+//
+// K/V staging.  The pool contract is token-granular (page_size 1), but the run allocator
+// (semi_pd_b200/memory_pool.py) places positions [k*128, k*128+128) of a request in 128 CONSECUTIVE
+// slots.  A tile of one kv head is then a strided 2-D box of the pool — 128 rows x 256 B, row
+// stride Hk*D*2 B — and the loader fetches it with TWO TMA tensor copies (cp.async.bulk.tensor,
+// 128-byte swizzle, 16 KB each) issued by one thread, completion counted on the slot's mbarrier.
+// The loader verifies on the device, per tile, that the 128 page-table entries really are
+// consecutive (and the tile is full); anything else — a foreign req_to_token, the reference
+// allocator's scattered slots, the ragged last tile of a sequence — takes the gather path:
+// 16-byte cp.async per row chunk through req_to_token into the same swizzled layout.
+// (tile::gather4, 4 rows x 128 B per instruction, was built and measured in round 1: correct,
+// but ~1 instruction per 27 clk per SM -> 36 GB/s per SM, below the cp.async gather's 47;
+// profiles/r01_decode_attention_loader_experiments.md.)
 #include <cuda.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 namespace spd {
 
@@ -67,6 +75,7 @@ struct DecodeParams {
   float* o_part;   // [b][Hq][splits][D]
   float* ml_part;  // [b][Hq][splits][2]
   int* counters;   // [b][Hk]
+  int use_tma;     // 0: always gather (SPD_ATTN_TMA=0)
 };
 
 struct DcItem {
@@ -144,10 +153,35 @@ __device__ __forceinline__ bool softmax_bar_or(bool pred) {
   return out != 0;
 }
 __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// barrier + AND-reduction over the 64 threads of one loader group (named barrier 2: K, 3: V)
+__device__ __forceinline__ bool loader_bar_and(bool pred, int is_v) {
+  uint32_t out;
+  if (is_v) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %1, 0;\n\t"
+        "barrier.cta.red.and.pred p, 3, 64, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(out)
+        : "r"(static_cast<uint32_t>(pred))
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %1, 0;\n\t"
+        "barrier.cta.red.and.pred p, 2, 64, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(out)
+        : "r"(static_cast<uint32_t>(pred))
+        : "memory");
+  }
+  return out != 0;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kDcThreads, 1)
-attn_decode_kernel(const DecodeParams p) {
+attn_decode_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const DecodeParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -292,24 +326,35 @@ attn_decode_kernel(const DecodeParams p) {
     int t = 0;
     // Page-table lookups run ONE TILE AHEAD of the gather (32 slots per thread), so the dependent
     // chain req_pool_indices -> req_to_token -> pool row is off the issue path.
-    auto lookup = [&](const DcCursor& cc, int* sl) {
+    // `base` = slot of the tile's first row when the tile is FULL (else -1): the candidate TMA row.
+    auto lookup = [&](const DcCursor& cc, int* sl, int& base) {
       const DcItem& it = cc.item;
       const int32_t* rtt0 = p.req_to_token + p.req_pool_indices[it.b] * p.rtt_stride;
-      const int tokb = it.t0 + cc.j * kDcTile + rsub;
+      const int tile0 = it.t0 + cc.j * kDcTile;
+      const int tokb = tile0 + rsub;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int tok = tokb + i * 4;
         sl[i] = tok < it.t1 ? __ldg(rtt0 + tok) : -1;
       }
+      base = (p.use_tma && tile0 + kDcTile <= it.t1) ? __ldg(rtt0 + tile0) : -1;
     };
-    int slot[32];
-    if (c.valid) lookup(c, slot);
+    const CUtensorMap* tmap = is_v ? &tmV : &tmK;
+    if (lt == 0) tma_prefetch_desc(tmap);
+    int slot[32], base = -1;
+    if (c.valid) lookup(c, slot, base);
     while (c.valid) {
       const int st = t % kDcStages;
       const int b = c.item.b, hk = c.item.hk, cj = c.j, citer = c.iter;
       c.next(p, s_len, total);
-      int nslot[32];
-      if (c.valid) lookup(c, nslot);
+      int nslot[32], nbase = -1;
+      if (c.valid) lookup(c, nslot, nbase);
+      // Are the tile's 128 page-table entries consecutive slots?  Each thread checks its 32 rows
+      // against the first row's slot; the group agrees through one barrier-with-AND.
+      bool contig = base > 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) contig &= (slot[i] == base + i * 4 + rsub);
+      if (p.use_tma) contig = loader_bar_and(contig, is_v);
       mbar_wait(&empty[st], ((t / kDcStages) & 1) ^ 1);
       if (!is_v && cj == 0) {
         // stage the G query rows of this (request, kv head) as the K-major B operand, in the same
@@ -321,21 +366,36 @@ attn_decode_kernel(const DecodeParams p) {
           cp_async16(smem_u32(sQ + (citer % kDcQBufs) * kDcQBytes + dc_small_off(r, chunk * 8)), src, true);
         }
       }
-      const int64_t col = static_cast<int64_t>(hk) * kDcD + chunk * 8;
-      const uint32_t dst = smem_u32(ring + st * kDcTileBytes);
+      if (contig) {
+        // one strided 2-D box of the pool: rows base .. base+127, the 128 columns of kv head hk,
+        // as two [128 x 64] boxes = the two 16 KB swizzle blocks of the slot
+        if (lt == 0) {
+          uint8_t* dst = ring + st * kDcTileBytes;
+          fence_proxy_async_smem();  // the slot may last have been written by the gather path
+          mbar_expect_tx_noarrive(&full[st], kDcTileBytes);
+          tma_load_2d(dst, tmap, &full[st], hk * kDcD, base, kEvictFirst);
+          tma_load_2d(dst + 16384, tmap, &full[st], hk * kDcD + 64, base, kEvictFirst);
+        }
+      } else {
+        const int64_t col = static_cast<int64_t>(hk) * kDcD + chunk * 8;
+        const uint32_t dst = smem_u32(ring + st * kDcTileBytes);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int row = i * 4 + rsub;
-        const bool valid = slot[i] >= 0;
-        const int64_t s64 = valid ? slot[i] : 0;
-        cp_async16(dst + dc_tile_off(row, chunk), pool + s64 * row_elems + col, valid);
+        for (int i = 0; i < 32; ++i) {
+          const int row = i * 4 + rsub;
+          const bool valid = slot[i] >= 0;
+          const int64_t s64 = valid ? slot[i] : 0;
+          cp_async16(dst + dc_tile_off(row, chunk), pool + s64 * row_elems + col, valid);
+        }
       }
       // completion is asynchronous: the barrier receives this thread's arrival when all of its
       // cp.asyncs above have landed — the loader never waits for data, only for a free slot, so
       // every slot of the ring can be in flight.  (The generic->async proxy fence is on the
       // consumer side, after its wait on this barrier.)
+      // (TMA tiles: the arrival below fires at once — or with the Q rows staged above — and the
+      // phase completes when the 32 KB the issuing thread announced have landed as well.)
       cp_async_mbar_arrive_noinc(&full[st]);
       ++t;
+      base = nbase;
 #pragma unroll
       for (int i = 0; i < 32; ++i) slot[i] = nslot[i];
     }
@@ -568,6 +628,15 @@ extern "C" int spd_attn_decode_paged(void* out, const void* q, const void* k_poo
     p.o_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 65536);
     p.ml_part = p.o_part + batch * num_q_heads * kDcMaxSplits * head_dim;
   }
+  // tensor maps over the pools: [slots, Hk*D] 16-bit, box 128 rows x 64 columns.  The C-ABI does
+  // not carry the pool's slot count; the row extent only bounds the coordinates the kernel may
+  // pass, and those are slot ids read from req_to_token, so the maximum is declared.
+  static const bool tma_on = []() { const char* e = getenv("SPD_ATTN_TMA"); return !(e && e[0] == '0'); }();
+  p.use_tma = tma_on ? 1 : 0;
+  CUtensorMap tk, tv;
+  const uint64_t row_elems = static_cast<uint64_t>(num_kv_heads) * head_dim;
+  if ((rc = get_tmap(&tk, k_pool, 1ull << 31, row_elems, row_elems, kDcTile))) return rc;
+  if ((rc = get_tmap(&tv, v_pool, 1ull << 31, row_elems, row_elems, kDcTile))) return rc;
   const int64_t total = pairs * splits;
   const int grid = static_cast<int>(total < sms ? total : sms);
   SPD_DISPATCH_DTYPE(dtype, {
@@ -577,7 +646,7 @@ extern "C" int spd_attn_decode_paged(void* out, const void* q, const void* k_poo
       SPD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDcSmem));
       configured = true;
     }
-    SPD_CUDA(launch(kern, dim3(grid), dim3(kDcThreads), kDcSmem, as_stream(stream), pdl_enabled(), p));
+    SPD_CUDA(launch(kern, dim3(grid), dim3(kDcThreads), kDcSmem, as_stream(stream), pdl_enabled(), tk, tv, p));
   });
   return 0;
 }

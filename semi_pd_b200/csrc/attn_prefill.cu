@@ -26,10 +26,13 @@
 //                    into TMEM over the first 32 columns of the S half they came from
 //                    (tcgen05.st) and feed the PV MMA as its A operand from TMEM;
 //                    epilogue O / l straight from TMEM to global memory;
-//   warp 8, warp 9   K / V loader: gather rows through req_to_token with 16-byte cp.async into
-//                    128-byte-swizzled smem; one 5-slot ring K_j V_j K_{j+1} ... runs ahead of the
-//                    consumer ACROSS items, so an item's first tiles are in flight while the
-//                    previous item drains;
+//   warp 8, warp 9   K / V loader into 128-byte-swizzled smem; one 5-slot ring K_j V_j K_{j+1} ...
+//                    runs ahead of the consumer ACROSS items, so an item's first tiles are in
+//                    flight while the previous item drains.  A tile whose 128 page-table entries
+//                    are consecutive slots (what the run allocator produces, memory_pool.py) is a
+//                    strided 2-D box of the pool and is fetched with two TMA tensor copies by one
+//                    lane; any other tile (scattered slots, the ragged tail of a sequence) is
+//                    gathered row by row through req_to_token with 16-byte cp.async;
 //   warp 10          MMA issuer: S_w,h = Q_w K_j[h]^T (both K-major in smem), O_w += P_w,h V_j[h] (P
 //                    from TMEM, V MN-major in smem); per warpgroup and half the order is PV(j,h)
 //                    then S(j+1,h) (which overwrites the columns P(j,h) lives in; tcgen05.mma
@@ -73,6 +76,7 @@ struct PrefillParams {
   int heads_x;     // item columns along the head axis
   int batch;
   int total_items;
+  int use_tma;  // 0: always gather (SPD_ATTN_TMA=0)
 };
 
 struct PfItem {
@@ -228,7 +232,8 @@ __device__ __forceinline__ float softmax_row_max(uint32_t ts, int kv0, int limit
 
 template <typename T>
 __global__ void __launch_bounds__(kPfThreads, 1)
-attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams p) {
+attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const PrefillParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -406,6 +411,12 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
           const int kv = j * kPfN + i * 2 + rsub;
           slot[i] = kv < it.kv_len ? __ldg(rtt + kv) : -1;
         }
+        // consecutive slots?  (full tile whose 128 entries are base, base+1, ...; warp vote)
+        const int base = (p.use_tma && (j + 1) * kPfN <= it.kv_len) ? __ldg(rtt + j * kPfN) : -1;
+        bool contig = base > 0;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) contig &= (slot[i] == base + i * 2 + rsub);
+        contig = __all_sync(0xffffffffu, contig);
         const uint32_t pos = 2 * t + is_v;
         const int st = pos % kPfSlots;
         const uint32_t epar = ((pos / kPfSlots) & 1) ^ 1;
@@ -421,6 +432,27 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const PrefillParams
           publish_after = false;
         }
         mbar_wait(&kv_empty[st], epar);
+        if (contig) {
+          // TMA: rows base .. base+127 of the pool, the 128 columns of kv head hk, as the slot's
+          // two 16 KB swizzle blocks; the 32 KB are counted on the slot's barrier next to the
+          // warp's 32 arrivals
+          if (lane == 0) {
+            uint8_t* dst = sKV + st * kTileBytes;
+            fence_proxy_async_smem();  // the slot may last have been written by the gather path
+            mbar_expect_tx_noarrive(&kv_full[st], kTileBytes);
+            tma_load_2d(dst, is_v ? &tmV : &tmK, &kv_full[st], it.hk * kPfD, base, kEvictNormal);
+            tma_load_2d(dst + 16384, is_v ? &tmV : &tmK, &kv_full[st], it.hk * kPfD + 64, base, kEvictNormal);
+          }
+          __syncwarp();
+          mbar_arrive(&kv_full[st]);
+          if (pending >= 0) {  // a gathered tile is still unpublished: no later group will cover it
+            cp_async_wait<0>();
+            fence_proxy_async_smem();
+            mbar_arrive(&kv_full[pending]);
+            pending = -1;
+          }
+          continue;
+        }
         const uint32_t dst = smem_u32(sKV + st * kTileBytes);
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
@@ -616,10 +648,17 @@ extern "C" int spd_attn_prefill_ragged(void* out, const void* q, const void* k_p
   const int64_t total = static_cast<int64_t>(p.tiles_x) * p.heads_x * batch;
   SPD_REQUIRE(total < (1ll << 30), SPD_E_SHAPE, "spd_attn_prefill_ragged: too many work items");
   p.total_items = static_cast<int>(total);
-  CUtensorMap tq;
+  CUtensorMap tq, tk, tv;
   if ((rc = get_tmap(&tq, q, static_cast<uint64_t>(total_tokens),
                      static_cast<uint64_t>(num_q_heads) * head_dim, static_cast<uint64_t>(q_stride), kPfM)))
     return rc;
+  // K/V pools as [slots, Hk*D] tensors, box 128 rows x 64 columns (the row extent only bounds the
+  // coordinates; they are slot ids taken from req_to_token)
+  static const bool tma_on = []() { const char* e = getenv("SPD_ATTN_TMA"); return !(e && e[0] == '0'); }();
+  p.use_tma = tma_on ? 1 : 0;
+  const uint64_t row_elems = static_cast<uint64_t>(num_kv_heads) * head_dim;
+  if ((rc = get_tmap(&tk, k_pool, 1ull << 31, row_elems, row_elems, kPfN))) return rc;
+  if ((rc = get_tmap(&tv, v_pool, 1ull << 31, row_elems, row_elems, kPfN))) return rc;
   const int sms = sm_budget > 0 ? sm_budget : device_sm_count_cached();
   const int grid = p.total_items < sms ? p.total_items : sms;
   SPD_DISPATCH_DTYPE(dtype, {
@@ -629,7 +668,7 @@ extern "C" int spd_attn_prefill_ragged(void* out, const void* q, const void* k_p
       SPD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmem));
       configured = true;
     }
-    SPD_CUDA(launch(kern, dim3(grid), dim3(kPfThreads), kPfSmem, as_stream(stream), pdl_enabled(), tq, p));
+    SPD_CUDA(launch(kern, dim3(grid), dim3(kPfThreads), kPfSmem, as_stream(stream), pdl_enabled(), tq, tk, tv, p));
   });
   return 0;
 }

@@ -425,6 +425,23 @@ class SmPartition:
             self._h = None
 
 
+_partitions = {}
+
+
+def get_partition(device: int, prefill_sms: int, decode_sms: int) -> SmPartition:
+    """Process-lifetime pool of SM partitions.  Green contexts and their streams are created once
+    per (device, split) and REUSED by every engine built afterwards: torch's caching allocator
+    and CUDA graphs keep referring to a stream long after the engine that used it is gone, so a
+    partition is never destroyed under them (doing so was measured to abort the process);
+    `SmPartition.close()` / spd_partition_destroy remain for embedders that own the streams'
+    whole lifetime."""
+    key = (int(device), int(prefill_sms), int(decode_sms))
+    part = _partitions.get(key)
+    if part is None:
+        part = _partitions[key] = SmPartition(device, prefill_sms, decode_sms)
+    return part
+
+
 def device_sm_count(device: int = 0) -> int:
     n = _C.c_int()
     check(lib.spd_device_sm_count(device, _C.byref(n)), "spd_device_sm_count")

@@ -618,7 +618,7 @@ class SemiPDEngine:
             # the reference's caps overlap (80 % + 100 %); green contexts are disjoint, so the two
             # percentages are normalised to a split of the device
             p_sms, d_sms = split_sms(total, p_pct, d_pct)
-            self.partition = ops.SmPartition(gpu_id, p_sms, d_sms)
+            self.partition = ops.get_partition(gpu_id, p_sms, d_sms)
             self.p_stream, self.d_stream = self.partition.prefill_stream, self.partition.decode_stream
             self.p_sms, self.d_sms = self.partition.prefill_sms, self.partition.decode_sms
         elif partition == "none":
@@ -727,18 +727,18 @@ class SemiPDEngine:
         for t in self.threads:
             t.join(timeout=timeout)
 
-    def shutdown(self, destroy_partition: bool = True):
-        """Stop both loops, drop everything that lives on the partition streams (CUDA graphs, the
-        workers' tensors, cached allocator blocks) and then destroy the green contexts
-        (`spd_partition_destroy`).  Under TP rank 0's call ends the loops of all ranks; the other
+    def shutdown(self):
+        """Stop both loops and drop everything the engine owns on the device: CUDA graphs, the
+        workers' tensors (weights, KV pool), the TP communicators.  The SM partition itself is a
+        process-lifetime object (ops.get_partition): the next engine on this GPU reuses its green
+        contexts and streams.  Under TP rank 0's call ends the loops of all ranks; the other
         ranks' calls wait for that."""
         if self._closed:
             return
         self._closed = True
         if self.tp_size == 1 or self.tp_rank == 0:
             self.decode.stop_flag.set()
-        for t in self.threads[:1]:
-            t.join(timeout=60)
+        self.threads[0].join(timeout=60)
         self.prefill.stop_flag.set()
         self.decode.stop_flag.set()
         for t in self.threads:
@@ -751,16 +751,9 @@ class SemiPDEngine:
             if mr.tp_comm is not None:
                 mr.tp_comm.close()
                 mr.tp_comm = None
-        if destroy_partition and self.partition is not None:
-            # nothing may still reference the partition's streams: the graphs are gone, the
-            # threads have exited, the device is idle; cached blocks of the stream-keyed
-            # allocator pools go back to the driver first
-            import gc
-            self.decode = self.prefill = None
-            self.d_worker = self.p_worker = None
-            gc.collect()
-            torch.cuda.synchronize()
-            torch.cuda.empty_cache()
-            self.p_stream = self.d_stream = None
-            self.partition.close()
-            self.partition = None
+            mr.model = None
+            mr.token_to_kv_pool = mr.token_to_kv_pool_allocator = mr.req_to_token_pool = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()

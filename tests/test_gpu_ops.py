@@ -239,6 +239,90 @@ def _paged(lens, Hk, D, dtype, extra=40, seed=0):
     return rtt, rpi, kp, vp
 
 
+def _paged_runs(lens, Hk, D, dtype, seed=0, mixed=False, run=128):
+    """Page tables as the run allocator lays them out (memory_pool.py): positions [k*128, k*128+128)
+    of a request are 128 consecutive slots, runs in random order across the pool.  `mixed` also
+    produces what a foreign allocator might: runs that start at arbitrary (unaligned) slots, tiles
+    with two entries swapped, and tiles that are consecutive except for their last entry — the
+    kernels must tell all of these apart from a TMA-able tile on the device."""
+    g = torch.Generator().manual_seed(seed)
+    B = len(lens)
+    n_runs = sum(-(-L // run) for L in lens) + 3
+    slots = n_runs * run + 1 + (64 if mixed else 0)
+    shift = 37 if mixed else 0
+    rtt = torch.zeros(B + 3, max(lens) + 8, dtype=torch.int32)
+    rpi = torch.randperm(B + 3, generator=g)[:B]
+    order = torch.randperm(n_runs, generator=g).tolist()
+    for b, L in enumerate(lens):
+        for k in range(-(-L // run)):
+            r = order.pop()
+            n = min(run, L - k * run)
+            ids = torch.arange(n, dtype=torch.int32) + (1 + shift + r * run)
+            if mixed and n == run and (b + k) % 3 == 1:
+                ids[[5, 77]] = ids[[77, 5]]                      # same slots, two swapped
+            elif mixed and n == run and (b + k) % 3 == 2:
+                ids[-1], ids[-2] = ids[-2].clone(), ids[-1].clone()  # consecutive but for the tail
+            rtt[rpi[b], k * run:k * run + n] = ids
+    kp = torch.randn(slots, Hk, D, generator=g).to(dtype)
+    vp = torch.randn(slots, Hk, D, generator=g).to(dtype)
+    return rtt, rpi, kp, vp
+
+
+@pytest.mark.parametrize("layout", ["runs", "mixed"])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("Hq,Hk", [(32, 8), (8, 1)])
+@pytest.mark.parametrize("lens", [[128], [17, 130, 1, 64, 700], [1500, 128, 129, 256, 384], [4000]],
+                         ids=["tile", "ragged", "long", "4k"])
+def test_attn_decode_run_layouts(ops, layout, dtype, Hq, Hk, lens):
+    """The TMA-staged K/V path (consecutive slots) and its on-device fallback decision."""
+    D = 128
+    rtt, rpi, kp, vp = _paged_runs(lens, Hk, D, dtype, seed=len(lens), mixed=layout == "mixed")
+    torch.manual_seed(5)
+    q = torch.randn(len(lens), Hq, D).to(dtype)
+    ref = O.attn_decode(q, kp, vp, rtt, rpi, lens, D ** -0.5, fp32=True)
+    sl = torch.tensor(lens, dtype=torch.int64, device=DEV)
+    args = (q.to(DEV).view(len(lens), -1), kp.to(DEV), vp.to(DEV), rtt.to(DEV), rpi.to(DEV), sl, Hq, Hk, D, D ** -0.5)
+    out = ops.attn_decode(*args, impl="tc")
+    err = (out.cpu().float().view(-1, Hq, D) - ref.float()).abs().max().item()
+    assert err < _tol(dtype, 2e-3, 1.6e-2), err
+    try:  # partition-sized grid: every CTA walks several items, TMA and gathered tiles interleaved
+        ops.set_sm_budget(8)
+        out8 = ops.attn_decode(*args, impl="tc")  # (a different KV split: not bit-comparable)
+        err8 = (out8.cpu().float().view(-1, Hq, D) - ref.float()).abs().max().item()
+        assert err8 < _tol(dtype, 2e-3, 1.6e-2), err8
+    finally:
+        ops.set_sm_budget(0)
+
+
+@pytest.mark.parametrize("layout", ["runs", "mixed"])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("Hq,Hk", [(32, 8), (8, 1)])
+@pytest.mark.parametrize("pre,ext", [([0], [128]), ([0, 0], [100, 257]), ([64, 0, 300], [200, 5, 129]),
+                                     ([0], [1024]), ([128, 256], [128, 512]), ([0, 40, 0], [700, 1024, 333])],
+                         ids=["tile", "two", "prefix", "1k", "aligned-prefix", "multi"])
+def test_attn_prefill_run_layouts(ops, layout, dtype, Hq, Hk, pre, ext):
+    D = 128
+    lens = [a + b for a, b in zip(pre, ext)]
+    rtt, rpi, kp, vp = _paged_runs(lens, Hk, D, dtype, seed=sum(lens), mixed=layout == "mixed")
+    torch.manual_seed(6)
+    T = sum(ext)
+    q = torch.randn(T, Hq, D).to(dtype)
+    ref = O.attn_extend(q, kp, vp, rtt, rpi, lens, pre, ext, D ** -0.5, fp32=True)
+    pre_t = torch.tensor(pre, dtype=torch.int32, device=DEV)
+    ext_t = torch.tensor(ext, dtype=torch.int32, device=DEV)
+    _, st = ops.compute_positions(pre_t, ext_t, T)
+    args = (q.to(DEV).view(T, -1), kp.to(DEV), vp.to(DEV), rtt.to(DEV), rpi.to(DEV), pre_t, ext_t, st, max(ext),
+            Hq, Hk, D, D ** -0.5)
+    out = ops.attn_prefill(*args, impl="tc")
+    err = (out.cpu().float().view(-1, Hq, D) - ref.float()).abs().max().item()
+    assert err < _tol(dtype, 2e-3, 1.6e-2), err
+    ops.set_sm_budget(8)
+    try:
+        assert torch.equal(ops.attn_prefill(*args, impl="tc"), out)  # the schedule must not change a bit
+    finally:
+        ops.set_sm_budget(0)
+
+
 @pytest.mark.parametrize("impl", ["tc", "simt"])
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("Hq,Hk", [(32, 8), (8, 1), (4, 4), (6, 2)])
@@ -344,3 +428,21 @@ def test_attn_properties_full_size(ops):
     rtt2 = mapping[rtt.long()].int()
     c = ops.attn_decode(q.to(DEV), kp2.to(DEV), vp2.to(DEV), rtt2.to(DEV), rpi.to(DEV), *args, impl="tc")
     assert torch.equal(a, c)
+    # (4) the same logical sequences re-housed in 128-slot runs (TMA-staged tiles) give the same
+    # bits as the scattered pool (gathered tiles): both paths fill smem identically
+    R = 128
+    runs_per = [-(-L // R) for L in lens]
+    order = torch.randperm(sum(runs_per)).tolist()
+    kp3 = torch.zeros(sum(runs_per) * R + 1, Hk, D, dtype=kp.dtype)
+    vp3 = torch.zeros_like(kp3)
+    rtt3 = torch.zeros_like(rtt)
+    for bi, L in enumerate(lens):
+        row = int(rpi[bi])
+        for k in range(runs_per[bi]):
+            n = min(R, L - k * R)
+            ids = torch.arange(n) + 1 + order.pop() * R
+            old = rtt[row, k * R:k * R + n].long()
+            kp3[ids], vp3[ids] = kp[old], vp[old]
+            rtt3[row, k * R:k * R + n] = ids.int()
+    d = ops.attn_decode(q.to(DEV), kp3.to(DEV), vp3.to(DEV), rtt3.to(DEV), rpi.to(DEV), *args, impl="tc")
+    assert torch.equal(a, d)
