@@ -56,7 +56,26 @@ struct GemmParams {
   int out_f32;
   float* ws;        // stream-K partials: one [col/4][lane][4] fp32 tile per CTA
   int* counters;    // stream-K: one 'partial published' flag per CTA
+  // grouped forms (spd_gemm_grouped; normal regime, whole tiles only)
+  const int* x_tile_group;  // rows mode: group (expert) of every 128-row x tile, < 0 = skip the tile;
+                            // the Y (weight) operand's rows start at group * y_group_rows
+  int64_t y_group_rows;
+  int y_tiles_per_group;    // cols mode: group = y tile / y_tiles_per_group; the X (activation)
+  int64_t x_group_cols;     // operand's columns start at group * x_group_cols
 };
+
+// (x column offset, y row offset) of a tile under the grouped forms; false = skip the tile
+__device__ __forceinline__ bool group_offsets(const GemmParams& p, int xt, int yt, int& xcol0, int& yrow0) {
+  xcol0 = 0;
+  yrow0 = 0;
+  if (p.x_tile_group) {
+    const int g = p.x_tile_group[xt];
+    if (g < 0) return false;
+    yrow0 = static_cast<int>(g * p.y_group_rows);
+  }
+  if (p.y_tiles_per_group > 0) xcol0 = static_cast<int>((yt / p.y_tiles_per_group) * p.x_group_cols);
+  return true;
+}
 
 template <int BN>
 __host__ __device__ constexpr int gemm_stage_bytes() { return (kBM + BN) * kBK * 2; }
@@ -200,18 +219,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       it.init(p);
       int tile, kb0, kb1, slot;
       while (it.next(tile, kb0, kb1, slot)) {
-        int xt, yt;
+        int xt, yt, xcol0, yrow0;
         tile_coords(p, tile, xt, yt);
+        if (!group_offsets(p, xt, yt, xcol0, yrow0)) continue;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], kXBytes + kYBytes);
-          tma_load_2d(sX + stage * kXBytes, &tmX, &full[stage], kb * kBK, xt * kBM, polX);
+          tma_load_2d(sX + stage * kXBytes, &tmX, &full[stage], xcol0 + kb * kBK, xt * kBM, polX);
           if constexpr (kEpi == SPD_EPI_SILU_MUL) {
-            tma_load_2d(sY + stage * kYBytes, &tmY, &full[stage], kb * kBK, yt * kBNOut, polY);
+            tma_load_2d(sY + stage * kYBytes, &tmY, &full[stage], kb * kBK, yrow0 + yt * kBNOut, polY);
             tma_load_2d(sY + stage * kYBytes + kYBytes / 2, &tmY, &full[stage], kb * kBK,
-                        static_cast<int>(p.y_rows_w) + yt * kBNOut, polY);
+                        yrow0 + static_cast<int>(p.y_rows_w) + yt * kBNOut, polY);
           } else {
-            tma_load_2d(sY + stage * kYBytes, &tmY, &full[stage], kb * kBK, yt * BN, polY);
+            tma_load_2d(sY + stage * kYBytes, &tmY, &full[stage], kb * kBK, yrow0 + yt * BN, polY);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -225,6 +245,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       it.init(p);
       int tile, kb0, kb1, slot;
       while (it.next(tile, kb0, kb1, slot)) {
+        if (p.x_tile_group) {  // grouped rows mode: all roles skip the same (unused) tiles
+          int xt, yt, a, b;
+          tile_coords(p, tile, xt, yt);
+          if (!group_offsets(p, xt, yt, a, b)) continue;
+        }
         // stream-K: slot 0 is reserved for the first segment (parked until the end if this CTA
         // owns that tile), every later segment goes through slot 1
         const int as = p.streamk ? (n == 0 ? 0 : 1) : (n & 1);
@@ -324,6 +349,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
     while (it.next(tile, kb0, kb1, slot)) {
       int xt, yt;
       tile_coords(p, tile, xt, yt);
+      if (p.x_tile_group && p.x_tile_group[xt] < 0) continue;
       const int as = p.streamk ? (n == 0 ? 0 : 1) : (n & 1);
       const int use = p.streamk ? (n == 0 ? 0 : n - 1) : (n >> 1);
       ++n;
@@ -693,6 +719,76 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
       SPD_DISPATCH_DTYPE(dtype, { return launch_gemm<T, 128, false, SPD_EPI_NONE>(tx, ty, p, grid, st); });
     }
   }
+  return 0;
+}
+
+
+int spd_gemm_grouped(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_t K, int64_t lda,
+                     int64_t ldw, int64_t ldc, int num_groups, const int32_t* tile_group,
+                     int64_t a_group_stride, int64_t a_cols, int dtype, int epilogue, int sm_budget,
+                     spd_stream_t stream) {
+  SPD_REQUIRE(C && A && W, SPD_E_BADARG, "spd_gemm_grouped: null pointer");
+  SPD_REQUIRE(M >= 0 && N > 0 && K > 0 && num_groups > 0, SPD_E_BADARG, "spd_gemm_grouped: bad sizes");
+  SPD_REQUIRE(dtype == SPD_BF16 || dtype == SPD_F16, SPD_E_BADARG, "spd_gemm_grouped: bad dtype %d", dtype);
+  SPD_REQUIRE(epilogue == SPD_EPI_NONE || epilogue == SPD_EPI_SILU_MUL, SPD_E_BADARG,
+              "spd_gemm_grouped: bad epilogue %d", epilogue);
+  SPD_REQUIRE(K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0 && a_group_stride % 8 == 0,
+              SPD_E_ALIGN, "spd_gemm_grouped: K, N, strides and leading dimensions must be multiples of 8");
+  SPD_REQUIRE(aligned16(A) && aligned16(W) && aligned16(C), SPD_E_ALIGN,
+              "spd_gemm_grouped: pointers must be 16-byte aligned");
+  if (M == 0) return 0;
+  const bool rows_mode = tile_group != nullptr;
+  cudaStream_t st = as_stream(stream);
+  const int sms = sm_budget > 0 ? sm_budget : device_sm_count_cached();
+  GemmParams p{};
+  p.C = C;
+  p.ldc = ldc;
+  p.kblocks = static_cast<int>((K + kBK - 1) / kBK);
+  p.x_rows = M;
+  p.x_tiles = static_cast<int>((M + kBM - 1) / kBM);
+  p.panel = 0;
+  CUtensorMap tx, ty;
+  int rc;
+  if (rows_mode) {
+    // MoE: rows of A sorted by expert in 128-row tiles; W = the experts' weights stacked
+    SPD_REQUIRE(a_group_stride == 0, SPD_E_BADARG, "spd_gemm_grouped: a_group_stride is a cols-mode argument");
+    p.x_tile_group = tile_group;
+    p.y_rows = N;
+    if ((rc = get_tmap(&tx, A, M, K, lda, kBM))) return rc;
+    if (epilogue == SPD_EPI_SILU_MUL) {
+      constexpr int BN = 256;
+      SPD_REQUIRE(N % 8 == 0, SPD_E_SHAPE, "spd_gemm_grouped: bad N");
+      p.y_group_rows = 2 * N;
+      p.y_rows_w = N;
+      p.y_tiles = static_cast<int>((N + BN / 2 - 1) / (BN / 2));
+      const int total = p.x_tiles * p.y_tiles;
+      const int grid = total < sms ? total : sms;
+      if ((rc = get_tmap(&ty, W, static_cast<uint64_t>(num_groups) * 2 * N, K, ldw, BN / 2))) return rc;
+      SPD_DISPATCH_DTYPE(dtype, { return launch_gemm<T, BN, false, SPD_EPI_SILU_MUL>(tx, ty, p, grid, st); });
+    }
+    constexpr int BN = 128;
+    p.y_group_rows = N;
+    p.y_tiles = static_cast<int>((N + BN - 1) / BN);
+    const int total = p.x_tiles * p.y_tiles;
+    const int grid = total < sms ? total : sms;
+    if ((rc = get_tmap(&ty, W, static_cast<uint64_t>(num_groups) * N, K, ldw, BN))) return rc;
+    SPD_DISPATCH_DTYPE(dtype, { return launch_gemm<T, BN, false, SPD_EPI_NONE>(tx, ty, p, grid, st); });
+  }
+  // cols mode (block diagonal): C[:, g*N:(g+1)*N] = A[:, g*a_group_stride : +K] * W[g*N:(g+1)*N, :K]^T
+  SPD_REQUIRE(epilogue == SPD_EPI_NONE, SPD_E_BADARG, "spd_gemm_grouped: no epilogue in cols mode");
+  SPD_REQUIRE(N % 128 == 0, SPD_E_SHAPE, "spd_gemm_grouped: cols mode needs N %% 128 == 0 (got %lld)", (long long)N);
+  SPD_REQUIRE(a_cols >= (num_groups - 1) * a_group_stride + K && lda >= a_cols, SPD_E_BADARG,
+              "spd_gemm_grouped: a_cols / lda too small");
+  constexpr int BN = 128;
+  p.y_rows = static_cast<int64_t>(num_groups) * N;
+  p.y_tiles = static_cast<int>(p.y_rows / BN);
+  p.y_tiles_per_group = static_cast<int>(N / BN);
+  p.x_group_cols = a_group_stride;
+  const int total = p.x_tiles * p.y_tiles;
+  const int grid = total < sms ? total : sms;
+  if ((rc = get_tmap(&tx, A, M, a_cols, lda, kBM))) return rc;
+  if ((rc = get_tmap(&ty, W, p.y_rows, K, ldw, BN))) return rc;
+  SPD_DISPATCH_DTYPE(dtype, { return launch_gemm<T, BN, false, SPD_EPI_NONE>(tx, ty, p, grid, st); });
   return 0;
 }
 
