@@ -88,7 +88,8 @@ int spd_rope_kvwrite(void* q, void* k, const void* v, void* k_pool, void* v_pool
                      int64_t tokens, int num_q_heads, int num_k_heads, int head_dim, int rot_dim,
                      int64_t q_stride, int64_t k_stride, int64_t v_stride, int interleave,
                      int dtype, spd_stream_t stream);
-/* k_pool[loc[t]] = k[t]; v_pool[loc[t]] = v[t] — set_kv_buffer alone (S/mem_cache/memory_pool.py:316-346) */
+/* k_pool[loc[t]] = k[t]; v_pool[loc[t]] = v[t] — set_kv_buffer alone (S/mem_cache/memory_pool.py:316-346).
+ * v and v_pool may both be NULL: single-buffer pools (MLATokenToKVPool.set_kv_buffer, :426-452). */
 int spd_kv_write(const void* k, const void* v, void* k_pool, void* v_pool, const int64_t* loc,
                  int64_t tokens, int64_t row_elems, int64_t k_stride, int64_t v_stride, int dtype,
                  spd_stream_t stream);
@@ -262,6 +263,71 @@ int spd_allreduce(spd_comm_t* comm, void* out, const void* in, int64_t count, in
 int spd_allgather(spd_comm_t* comm, void* out, const void* in, int64_t bytes_per_rank,
                   spd_stream_t stream);
 int spd_comm_destroy(spd_comm_t* comm);
+
+/* ---------------------------------------------------------------------------------------------
+ * DeepSeek-V2-Lite path (BASELINE configs[3]): absorbed MLA attention over the latent KV pool,
+ * grouped GEMMs and the MoE plumbing.
+ * ------------------------------------------------------------------------------------------- */
+/* Grouped GEMM on the tcgen05 kernel of spd_gemm (normal regime, 128-row tiles).
+ * rows mode (tile_group != NULL) — the two expert GEMMs of the fused MoE
+ *   (S/layers/moe/fused_moe_triton/fused_moe.py:961-1168): A [M, K] holds the routed tokens sorted by
+ *   expert in 128-row tiles (spd_moe_align / spd_moe_gather), tile_group[i] = expert of rows
+ *   [128 i, 128 i + 128) or < 0 (unused tile, skipped); W = the experts' weights stacked,
+ *   [num_groups * N, K] — with SPD_EPI_SILU_MUL [num_groups * 2N, K], gate rows || up rows per expert;
+ *   C [M, N].  a_group_stride must be 0.
+ * cols mode (tile_group == NULL) — block-diagonal products, the absorbed-MLA BMMs
+ *   torch.bmm(q_nope, w_kc) / torch.bmm(attn_out, w_vc) (S/models/deepseek_v2.py:667,702):
+ *   C[:, g*N:(g+1)*N] = A[:, g*a_group_stride : g*a_group_stride + K] * W[g*N:(g+1)*N, :K]^T,
+ *   A [M, a_cols] with row stride lda, N % 128 == 0, K % 64 == 0.  c_group_stride > 0 places group g's
+ *   N output columns at column g * c_group_stride of C instead of g * N.
+ * w_group_col_stride > 0 (rows mode, no epilogue): the experts' weights are concatenated along K
+ *   instead of stacked — W [N, num_groups * w_group_col_stride], expert g = columns
+ *   [g * stride, g * stride + K) — the layout the decode-sized dense path multiplies as ONE GEMM. */
+int spd_gemm_grouped(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_t K, int64_t lda,
+                     int64_t ldw, int64_t ldc, int num_groups, const int32_t* tile_group,
+                     int64_t a_group_stride, int64_t a_cols, int64_t c_group_stride, int64_t w_group_col_stride,
+                     int dtype, int epilogue, int sm_budget, spd_stream_t stream);
+/* Router: softmax over the experts (fp32) + greedy top-k; weights = prob (renormalised over the k
+ * if renormalize) * scale.  logits [tokens, num_experts] 16-bit.  replaces select_experts /
+ * fused_topk (S/layers/moe/topk.py:79-120,128-163). */
+int spd_moe_route(int32_t* topk_ids, float* topk_w, const void* logits, int64_t tokens, int num_experts,
+                  int top_k, float scale, int renormalize, int dtype, spd_stream_t stream);
+/* Expert alignment: sorts the tokens*top_k routing entries by expert, every expert padded to whole
+ * 128-row tiles.  row_token[max_rows]: source token of each sorted row (-1 = padding);
+ * inv_pos[tokens*top_k]: sorted row of entry (token, j); tile_group[max_rows/128]: expert per tile
+ * (-1 = unused).  max_rows >= spd_moe_align_rows().  replaces moe_align_block_size
+ * (K/csrc/moe/moe_align_kernel.cu:28,44). */
+int64_t spd_moe_align_rows(int64_t tokens, int top_k, int num_experts);
+int spd_moe_align(int32_t* row_token, int32_t* inv_pos, int32_t* tile_group, const int32_t* topk_ids,
+                  int64_t tokens, int top_k, int num_experts, int64_t max_rows, spd_stream_t stream);
+/* xs[r, :] = x[row_token[r], :] (zeros for padding rows) */
+int spd_moe_gather(void* xs, const void* x, const int32_t* row_token, int64_t rows, int64_t dim,
+                   int64_t x_stride, int dtype, spd_stream_t stream);
+/* out[t, :] = (shared ? shared[t, :] : 0) + sum_j topk_w[t, j] * y[inv_pos[t*top_k + j], :]
+ * (the weighted sum of fused_moe + the shared experts' output, S/models/deepseek_v2.py:205-218) */
+int spd_moe_combine(void* out, const void* y, const void* shared, const int32_t* inv_pos, const float* topk_w,
+                    int64_t tokens, int top_k, int64_t dim, int dtype, spd_stream_t stream);
+/* Decode-sized batches run every expert as two plain spd_gemm calls over the stacked weights;
+ * between them: act[t, e*inter + i] = w(t, e) * silu(gate_up[t, e, i]) * gate_up[t, e, inter + i],
+ * w(t, e) = 0 for experts token t did not select.  gate_up [tokens, num_experts * 2 * inter]. */
+int spd_moe_dense_act(void* act, const void* gate_up, const int32_t* topk_ids, const float* topk_w,
+                      int64_t tokens, int top_k, int num_experts, int64_t inter, int dtype,
+                      spd_stream_t stream);
+/* Absorbed MLA attention (MQA over the latent pool), decode (seq_lens != NULL: one query per request
+ * over its seq_lens[b] rows) or ragged extend (seq_lens == NULL: query token j of request r, row
+ * extend_start_loc[r] + j of q, attends keys 0 .. prefix_lens[r] + j).  kv_pool [slots, kv_lora_rank +
+ * rope_dim] = MLATokenToKVPool rows (S/mem_cache/memory_pool.py:379-452); K = the whole row, V = its
+ * first kv_lora_rank columns; q [tokens, H, kv_lora_rank + rope_dim] (q_nope already multiplied by
+ * w_kc), out [tokens, H, kv_lora_rank].  replaces DeepseekV2AttentionMLA.forward_absorb's attention
+ * call (S/models/deepseek_v2.py:684-700 → S/layers/attention/triton_ops/decode_attention.py:235-470,
+ * extend_attention.py:291-410). */
+int64_t spd_attn_mla_workspace_bytes(int num_heads, int kv_lora_rank);
+int spd_attn_mla(void* out, const void* q, const void* kv_pool, const int32_t* req_to_token,
+                 const int64_t* req_pool_indices, const int64_t* seq_lens, const int32_t* prefix_lens,
+                 const int32_t* extend_start_loc, int64_t batch, int64_t total_tokens, int num_heads,
+                 int kv_lora_rank, int rope_dim, int64_t q_stride, int64_t out_stride,
+                 int64_t req_to_token_stride, float sm_scale, int dtype, void* workspace,
+                 int64_t workspace_bytes, int sm_budget, spd_stream_t stream);
 
 #ifdef __cplusplus
 }

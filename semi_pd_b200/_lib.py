@@ -75,6 +75,17 @@ SIGNATURES = {
     "spd_comm_destroy": (_i, [_p]),
     "spd_argmax_partial_f32": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p]),
     "spd_argmax_merge": (_i, [_p, _p, _i, _i64, _p]),
+    "spd_gemm_grouped": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i, _p, _i64, _i64, _i64, _i64, _i,
+                              _i, _i, _p]),
+    "spd_moe_route": (_i, [_p, _p, _p, _i64, _i, _i, _f, _i, _i, _p]),
+    "spd_moe_align_rows": (_i64, [_i64, _i, _i]),
+    "spd_moe_align": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i64, _p]),
+    "spd_moe_gather": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _p]),
+    "spd_moe_combine": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i64, _i, _p]),
+    "spd_moe_dense_act": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i64, _i, _p]),
+    "spd_attn_mla_workspace_bytes": (_i64, [_i, _i]),
+    "spd_attn_mla": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i64, _i64, _i64, _f, _i, _p,
+                          _i64, _i, _p]),
     "spd_attn_prefill_simt": (
         _i,
         [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i, _i, _i64, _i64, _i64, _f, _i, _p],

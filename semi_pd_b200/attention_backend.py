@@ -98,6 +98,7 @@ class SpdAttnBackend(AttentionBackend):
         self.device = model_runner.device
         self.num_q_heads = model_runner.model_config.num_attention_heads // model_runner.tp_size
         self.head_dim = model_runner.model_config.head_dim
+        self.is_mla = getattr(model_runner.model_config, "model_type", "llama") == "deepseek_v2"
         # "tc" = tcgen05 kernels (the product path, head_dim 128); "simt" exists for bring-up /
         # cross-checks and serves the head_dim-64 plumbing model (OPT-125m, BASELINE configs[0])
         self.impl = os.environ.get("SPD_ATTN_IMPL", "tc" if self.head_dim == 128 else "simt")
@@ -106,6 +107,14 @@ class SpdAttnBackend(AttentionBackend):
         # is allocated exactly ONCE here and never replaced: the kernel only splits when
         # batch x kv_heads is below the SM count, i.e. for at most ceil(SMs / kv_heads) requests,
         # which bounds the scratch whatever batch size an eager step later runs with.
+        if self.is_mla:
+            # absorbed MLA: one latent "kv head"; the split-KV scratch of spd_attn_mla (bounded by
+            # 2 x SMs query tokens, see csrc/attn_mla.cu) — allocated once, like the one below
+            cfg = model_runner.model_config
+            need = ops.lib.spd_attn_mla_workspace_bytes(self.num_q_heads, cfg.kv_lora_rank)
+            self.mla_workspace = torch.zeros((need,), dtype=torch.uint8, device=self.device)
+            self.decode_workspace = None
+            return
         num_kv_heads = model_runner.model_config.get_num_kv_heads(model_runner.tp_size)
         sms = ops.device_sm_count(self.device.index or 0)
         self.split_rows = -(-sms // max(num_kv_heads, 1)) + 1
@@ -156,3 +165,19 @@ class SpdAttnBackend(AttentionBackend):
             forward_batch.req_pool_indices, forward_batch.seq_lens, layer.tp_q_head_num,
             layer.tp_k_head_num, layer.head_dim, layer.scaling, impl=self.impl,
             workspace=self.decode_workspace)
+
+    def forward_mla(self, q_lat, layer: RadixAttention, forward_batch: ForwardBatch):
+        """Absorbed MLA attention over the latent pool (DeepseekV2AttentionMLA.forward_absorb's
+        attention call, models/deepseek_v2.py:684-700): q_lat [T, H * (kv_lora + rope)] →
+        [T, H * kv_lora].  The latent rows of this batch are already in the pool."""
+        pool = forward_batch.token_to_kv_pool
+        kv = pool.get_key_buffer(layer.layer_id)
+        rope = layer.head_dim - layer.v_head_dim
+        common = dict(num_heads=layer.tp_q_head_num, kv_lora_rank=layer.v_head_dim, rope_dim=rope,
+                      sm_scale=layer.scaling, workspace=self.mla_workspace)
+        if forward_batch.forward_mode.is_decode():
+            return ops.attn_mla(q_lat, kv, forward_batch.req_to_token_pool.req_to_token,
+                                forward_batch.req_pool_indices, seq_lens=forward_batch.seq_lens, **common)
+        return ops.attn_mla(q_lat, kv, forward_batch.req_to_token_pool.req_to_token,
+                            forward_batch.req_pool_indices, prefix_lens=forward_batch.extend_prefix_lens,
+                            extend_start_loc=forward_batch.extend_start_loc, **common)

@@ -46,6 +46,20 @@ class ModelConfig:
     layer_norm_eps: float = 1e-5
     # hf_eos_token_id of the reference's ModelConfig (honoured when a request sets ignore_eos=False)
     eos_token_ids: Optional[List[int]] = None
+    # DeepSeek-V2 (model_type "deepseek_v2"): MLA + MoE (models/deepseek_v2.py)
+    q_lora_rank: Optional[int] = None
+    kv_lora_rank: int = 512
+    qk_nope_head_dim: int = 128
+    qk_rope_head_dim: int = 64
+    v_head_dim: int = 128
+    n_routed_experts: Optional[int] = None
+    num_experts_per_tok: int = 6
+    n_shared_experts: int = 2
+    moe_intermediate_size: int = 1408
+    first_k_dense_replace: int = 1
+    moe_layer_freq: int = 1
+    routed_scaling_factor: float = 1.0
+    norm_topk_prob: bool = False
 
     @property
     def context_len(self) -> int:
@@ -71,6 +85,16 @@ _PRESETS = {
     "opt-125m": dict(model_type="opt", hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
                      num_attention_heads=12, num_key_value_heads=12, head_dim=64, vocab_size=50272,
                      max_position_embeddings=2048, hidden_act="relu", tie_word_embeddings=True),
+    # BASELINE configs[3]: deepseek-ai/DeepSeek-V2-Lite (15.7 B parameters, 2.4 B active)
+    "deepseek-v2-lite": dict(model_type="deepseek_v2", hidden_size=2048, intermediate_size=10944,
+                             num_hidden_layers=27, num_attention_heads=16, num_key_value_heads=16,
+                             head_dim=192, vocab_size=102400, rms_norm_eps=1e-6, rope_theta=10000.0,
+                             max_position_embeddings=163840, n_routed_experts=64, num_experts_per_tok=6,
+                             n_shared_experts=2, moe_intermediate_size=1408, first_k_dense_replace=1,
+                             kv_lora_rank=512, qk_nope_head_dim=128, qk_rope_head_dim=64, v_head_dim=128,
+                             routed_scaling_factor=1.0, norm_topk_prob=False, eos_token_ids=[100001],
+                             rope_scaling=dict(type="yarn", factor=40.0, beta_fast=32, beta_slow=1, mscale=0.707,
+                                               mscale_all_dim=0.707, original_max_position_embeddings=4096)),
     # one 8B-shaped layer pair: exhaustive parity at real head/FFN shapes
     "llama-3-8b-2layer": dict(num_hidden_layers=2, vocab_size=4096),
 }

@@ -267,9 +267,13 @@ kv_write_kernel(const T* __restrict__ k, const T* __restrict__ v, T* __restrict_
   const Vec8* vs = reinterpret_cast<const Vec8*>(v + t * v_stride);
   Vec8* kd = reinterpret_cast<Vec8*>(k_pool + slot * row_elems);
   Vec8* vd = reinterpret_cast<Vec8*>(v_pool + slot * row_elems);
-  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-    kd[i] = ks[i];
-    vd[i] = vs[i];
+  if (v == nullptr) {  // single-buffer pools (MLA latent rows): only the k side exists
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) kd[i] = ks[i];
+  } else {
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      kd[i] = ks[i];
+      vd[i] = vs[i];
+    }
   }
   griddep_launch_dependents();
 }
@@ -653,7 +657,8 @@ int spd_rope_kvwrite(void* q, void* k, const void* v, void* k_pool, void* v_pool
 int spd_kv_write(const void* k, const void* v, void* k_pool, void* v_pool, const int64_t* loc,
                  int64_t tokens, int64_t row_elems, int64_t k_stride, int64_t v_stride, int dtype,
                  spd_stream_t stream) {
-  SPD_REQUIRE(k && v && k_pool && v_pool && loc, SPD_E_BADARG, "spd_kv_write: null pointer");
+  SPD_REQUIRE(k && k_pool && loc && ((v == nullptr) == (v_pool == nullptr)), SPD_E_BADARG,
+              "spd_kv_write: null pointer (v and v_pool may both be NULL for a single-buffer pool)");
   SPD_REQUIRE(tokens >= 0 && row_elems > 0, SPD_E_BADARG, "spd_kv_write: bad sizes");
   SPD_REQUIRE(row_elems % 8 == 0 && k_stride % 8 == 0 && v_stride % 8 == 0 && aligned16(k) &&
                   aligned16(v) && aligned16(k_pool) && aligned16(v_pool),

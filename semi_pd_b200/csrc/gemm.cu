@@ -60,18 +60,23 @@ struct GemmParams {
   const int* x_tile_group;  // rows mode: group (expert) of every 128-row x tile, < 0 = skip the tile;
                             // the Y (weight) operand's rows start at group * y_group_rows
   int64_t y_group_rows;
+  int64_t y_group_cols;     // rows mode, K-concatenated weights: the Y operand's COLUMNS start at group * y_group_cols
   int y_tiles_per_group;    // cols mode: group = y tile / y_tiles_per_group; the X (activation)
-  int64_t x_group_cols;     // operand's columns start at group * x_group_cols
+  int64_t x_group_cols;     // operand's columns start at group * x_group_cols,
+  int64_t c_group_cols;     // and the group's output columns at group * c_group_cols (0: contiguous)
 };
 
 // (x column offset, y row offset) of a tile under the grouped forms; false = skip the tile
-__device__ __forceinline__ bool group_offsets(const GemmParams& p, int xt, int yt, int& xcol0, int& yrow0) {
+__device__ __forceinline__ bool group_offsets(const GemmParams& p, int xt, int yt, int& xcol0, int& yrow0,
+                                              int& ycol0) {
   xcol0 = 0;
   yrow0 = 0;
+  ycol0 = 0;
   if (p.x_tile_group) {
     const int g = p.x_tile_group[xt];
     if (g < 0) return false;
     yrow0 = static_cast<int>(g * p.y_group_rows);
+    ycol0 = static_cast<int>(g * p.y_group_cols);
   }
   if (p.y_tiles_per_group > 0) xcol0 = static_cast<int>((yt / p.y_tiles_per_group) * p.x_group_cols);
   return true;
@@ -219,19 +224,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       it.init(p);
       int tile, kb0, kb1, slot;
       while (it.next(tile, kb0, kb1, slot)) {
-        int xt, yt, xcol0, yrow0;
+        int xt, yt, xcol0, yrow0, ycol0;
         tile_coords(p, tile, xt, yt);
-        if (!group_offsets(p, xt, yt, xcol0, yrow0)) continue;
+        if (!group_offsets(p, xt, yt, xcol0, yrow0, ycol0)) continue;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], kXBytes + kYBytes);
           tma_load_2d(sX + stage * kXBytes, &tmX, &full[stage], xcol0 + kb * kBK, xt * kBM, polX);
           if constexpr (kEpi == SPD_EPI_SILU_MUL) {
-            tma_load_2d(sY + stage * kYBytes, &tmY, &full[stage], kb * kBK, yrow0 + yt * kBNOut, polY);
-            tma_load_2d(sY + stage * kYBytes + kYBytes / 2, &tmY, &full[stage], kb * kBK,
+            tma_load_2d(sY + stage * kYBytes, &tmY, &full[stage], ycol0 + kb * kBK, yrow0 + yt * kBNOut, polY);
+            tma_load_2d(sY + stage * kYBytes + kYBytes / 2, &tmY, &full[stage], ycol0 + kb * kBK,
                         yrow0 + static_cast<int>(p.y_rows_w) + yt * kBNOut, polY);
           } else {
-            tma_load_2d(sY + stage * kYBytes, &tmY, &full[stage], kb * kBK, yrow0 + yt * BN, polY);
+            tma_load_2d(sY + stage * kYBytes, &tmY, &full[stage], ycol0 + kb * kBK, yrow0 + yt * BN, polY);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -246,9 +251,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       int tile, kb0, kb1, slot;
       while (it.next(tile, kb0, kb1, slot)) {
         if (p.x_tile_group) {  // grouped rows mode: all roles skip the same (unused) tiles
-          int xt, yt, a, b;
+          int xt, yt, a, b, c;
           tile_coords(p, tile, xt, yt);
-          if (!group_offsets(p, xt, yt, a, b)) continue;
+          if (!group_offsets(p, xt, yt, a, b, c)) continue;
         }
         // stream-K: slot 0 is reserved for the first segment (parked until the end if this CTA
         // owns that tile), every later segment goes through slot 1
@@ -288,7 +293,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
     auto store_chunk = [&](int xt, int yt, int c, const float* v) {
       if constexpr (!kSwap) {
         const int64_t m = static_cast<int64_t>(xt) * kBM + row;
-        const int64_t n0 = static_cast<int64_t>(yt) * kBNOut + c;
+        int64_t n0 = static_cast<int64_t>(yt) * kBNOut + c;
+        if (p.c_group_cols > 0) {  // cols mode with strided output groups
+          const int g = yt / p.y_tiles_per_group;
+          n0 = g * p.c_group_cols + static_cast<int64_t>(yt - g * p.y_tiles_per_group) * kBNOut + c;
+        }
         if (m < p.x_rows) {
           if (p.out_f32) {
             float* dst = reinterpret_cast<float*>(p.C) + m * p.ldc + n0;
@@ -725,8 +734,8 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
 
 int spd_gemm_grouped(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_t K, int64_t lda,
                      int64_t ldw, int64_t ldc, int num_groups, const int32_t* tile_group,
-                     int64_t a_group_stride, int64_t a_cols, int dtype, int epilogue, int sm_budget,
-                     spd_stream_t stream) {
+                     int64_t a_group_stride, int64_t a_cols, int64_t c_group_stride, int64_t w_group_col_stride,
+                     int dtype, int epilogue, int sm_budget, spd_stream_t stream) {
   SPD_REQUIRE(C && A && W, SPD_E_BADARG, "spd_gemm_grouped: null pointer");
   SPD_REQUIRE(M >= 0 && N > 0 && K > 0 && num_groups > 0, SPD_E_BADARG, "spd_gemm_grouped: bad sizes");
   SPD_REQUIRE(dtype == SPD_BF16 || dtype == SPD_F16, SPD_E_BADARG, "spd_gemm_grouped: bad dtype %d", dtype);
@@ -751,7 +760,10 @@ int spd_gemm_grouped(void* C, const void* A, const void* W, int64_t M, int64_t N
   int rc;
   if (rows_mode) {
     // MoE: rows of A sorted by expert in 128-row tiles; W = the experts' weights stacked
-    SPD_REQUIRE(a_group_stride == 0, SPD_E_BADARG, "spd_gemm_grouped: a_group_stride is a cols-mode argument");
+    SPD_REQUIRE(a_group_stride == 0 && c_group_stride == 0, SPD_E_BADARG,
+                "spd_gemm_grouped: a_group_stride / c_group_stride are cols-mode arguments");
+    SPD_REQUIRE(w_group_col_stride % 8 == 0 && (w_group_col_stride == 0 || epilogue == SPD_EPI_NONE),
+                SPD_E_BADARG, "spd_gemm_grouped: bad w_group_col_stride");
     p.x_tile_group = tile_group;
     p.y_rows = N;
     if ((rc = get_tmap(&tx, A, M, K, lda, kBM))) return rc;
@@ -767,16 +779,30 @@ int spd_gemm_grouped(void* C, const void* A, const void* W, int64_t M, int64_t N
       SPD_DISPATCH_DTYPE(dtype, { return launch_gemm<T, BN, false, SPD_EPI_SILU_MUL>(tx, ty, p, grid, st); });
     }
     constexpr int BN = 128;
-    p.y_group_rows = N;
     p.y_tiles = static_cast<int>((N + BN - 1) / BN);
     const int total = p.x_tiles * p.y_tiles;
     const int grid = total < sms ? total : sms;
-    if ((rc = get_tmap(&ty, W, static_cast<uint64_t>(num_groups) * N, K, ldw, BN))) return rc;
+    if (w_group_col_stride > 0) {
+      // weights concatenated along K: W [N, num_groups * w_group_col_stride], expert g = columns
+      // [g * stride, g * stride + K).  K must be a whole number of 64-column blocks, or the last
+      // block would read into the next expert.
+      SPD_REQUIRE(K % kBK == 0, SPD_E_SHAPE, "spd_gemm_grouped: K %% 64 != 0 with K-concatenated weights");
+      p.y_group_cols = w_group_col_stride;
+      if ((rc = get_tmap(&ty, W, N, static_cast<uint64_t>(num_groups) * w_group_col_stride, ldw, BN))) return rc;
+    } else {
+      p.y_group_rows = N;
+      if ((rc = get_tmap(&ty, W, static_cast<uint64_t>(num_groups) * N, K, ldw, BN))) return rc;
+    }
     SPD_DISPATCH_DTYPE(dtype, { return launch_gemm<T, BN, false, SPD_EPI_NONE>(tx, ty, p, grid, st); });
   }
   // cols mode (block diagonal): C[:, g*N:(g+1)*N] = A[:, g*a_group_stride : +K] * W[g*N:(g+1)*N, :K]^T
-  SPD_REQUIRE(epilogue == SPD_EPI_NONE, SPD_E_BADARG, "spd_gemm_grouped: no epilogue in cols mode");
-  SPD_REQUIRE(N % 128 == 0, SPD_E_SHAPE, "spd_gemm_grouped: cols mode needs N %% 128 == 0 (got %lld)", (long long)N);
+  SPD_REQUIRE(epilogue == SPD_EPI_NONE && w_group_col_stride == 0, SPD_E_BADARG,
+              "spd_gemm_grouped: no epilogue / K-concatenated weights in cols mode");
+  SPD_REQUIRE(c_group_stride == 0 || (c_group_stride >= N && c_group_stride % 8 == 0), SPD_E_BADARG,
+              "spd_gemm_grouped: bad c_group_stride");
+  SPD_REQUIRE(N % 128 == 0 && K % kBK == 0, SPD_E_SHAPE,
+              "spd_gemm_grouped: cols mode needs N %% 128 == 0 and K %% 64 == 0 (got N=%lld K=%lld)",
+              (long long)N, (long long)K);
   SPD_REQUIRE(a_cols >= (num_groups - 1) * a_group_stride + K && lda >= a_cols, SPD_E_BADARG,
               "spd_gemm_grouped: a_cols / lda too small");
   constexpr int BN = 128;
@@ -784,6 +810,7 @@ int spd_gemm_grouped(void* C, const void* A, const void* W, int64_t M, int64_t N
   p.y_tiles = static_cast<int>(p.y_rows / BN);
   p.y_tiles_per_group = static_cast<int>(N / BN);
   p.x_group_cols = a_group_stride;
+  p.c_group_cols = c_group_stride;
   const int total = p.x_tiles * p.y_tiles;
   const int grid = total < sms ? total : sms;
   if ((rc = get_tmap(&tx, A, M, a_cols, lda, kBM))) return rc;

@@ -335,3 +335,45 @@ class MHATokenToKVPool(KVCache):
         if cache_k.dtype != self.dtype:
             raise RuntimeError("KV cache dtype conversion is not on the semi-PD path")
         ops.kv_write(cache_k, cache_v, self.k_buffer[layer_id], self.v_buffer[layer_id], loc)
+
+
+class MLATokenToKVPool(KVCache):
+    """One latent buffer per layer, rows [kv_a_normed(kv_lora_rank) || k_pe_roped(qk_rope_head_dim)]
+    (python/sglang/srt/mem_cache/memory_pool.py:379-452): `kv_buffer[l]` is [size + 1, 1, 576] for
+    DeepSeek-V2-Lite — 1152 B per token per layer.  Keys are the whole row, values its first
+    kv_lora_rank columns (`get_value_buffer` returns that view, :426-433)."""
+
+    def __init__(self, size: int, page_size: int, dtype: torch.dtype, kv_lora_rank: int, qk_rope_head_dim: int,
+                 layer_num: int, device: str, enable_memory_saver: bool = False,
+                 bypass_create_buffers: bool = False):
+        if page_size != 1:
+            raise NotImplementedError("semi-PD path is token-granular: page_size must be 1")
+        self.size = size
+        self.page_size = page_size
+        self.dtype = dtype
+        self.store_dtype = dtype
+        self.device = device
+        self.kv_lora_rank = kv_lora_rank
+        self.qk_rope_head_dim = qk_rope_head_dim
+        self.layer_num = layer_num
+        self.head_num = 1
+        self.head_dim = kv_lora_rank + qk_rope_head_dim
+        self._slab = torch.zeros((layer_num, size + page_size, 1, self.head_dim), dtype=dtype, device=device)
+        self.kv_buffer = [self._slab[i] for i in range(layer_num)]
+
+    def get_kv_size_bytes(self):
+        return self._slab.numel() * self._slab.element_size()
+
+    def get_key_buffer(self, layer_id: int):
+        return self.kv_buffer[layer_id]
+
+    def get_value_buffer(self, layer_id: int):
+        return self.kv_buffer[layer_id][..., : self.kv_lora_rank]
+
+    def get_kv_buffer(self, layer_id: int):
+        return self.get_key_buffer(layer_id), self.get_value_buffer(layer_id)
+
+    def set_kv_buffer(self, layer, loc: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor = None):
+        if cache_k.dtype != self.dtype:
+            raise RuntimeError("KV cache dtype conversion is not on the semi-PD path")
+        ops.kv_write_single(cache_k, self.kv_buffer[layer.layer_id], loc)

@@ -26,7 +26,7 @@ from .distributed import TpComm, init_distributed_environment, set_current_comm
 from .forward_batch_info import ForwardBatch, ForwardMode, LogitsProcessorOutput
 from .layers import Sampler
 from .llama import LlamaForCausalLM
-from .memory_pool import MHATokenToKVPool, ReqToTokenPool, TokenToKVPoolAllocator
+from .memory_pool import MHATokenToKVPool, MLATokenToKVPool, ReqToTokenPool, TokenToKVPoolAllocator
 
 logger = logging.getLogger(__name__)
 
@@ -95,6 +95,9 @@ class ModelRunner:
         if getattr(self.model_config, "model_type", "llama") == "opt":
             from .opt import OPTForCausalLM
             self.model = OPTForCausalLM(self.model_config, dtype=self.dtype, device=self.device)
+        elif self.model_config.model_type == "deepseek_v2":
+            from .deepseek_v2 import DeepseekV2ForCausalLM
+            self.model = DeepseekV2ForCausalLM(self.model_config, dtype=self.dtype, device=self.device)
         else:
             self.model = LlamaForCausalLM(self.model_config, dtype=self.dtype, device=self.device)
         if self.server_args.load_format == "dummy":
@@ -107,8 +110,11 @@ class ModelRunner:
         """model_runner.py:924-949: tokens that fit in mem_fraction_static of the device after
         the weights."""
         cfg = self.model_config
-        cell = (cfg.get_num_kv_heads(self.tp_size) * cfg.head_dim * cfg.num_hidden_layers * 2 *
-                torch.tensor([], dtype=self.kv_cache_dtype).element_size())
+        esz = torch.tensor([], dtype=self.kv_cache_dtype).element_size()
+        if getattr(cfg, "model_type", "llama") == "deepseek_v2":
+            cell = (cfg.kv_lora_rank + cfg.qk_rope_head_dim) * cfg.num_hidden_layers * esz  # model_runner.py:930-936
+        else:
+            cell = cfg.get_num_kv_heads(self.tp_size) * cfg.head_dim * cfg.num_hidden_layers * 2 * esz
         free, total = torch.cuda.mem_get_info(self.device)
         frac = self.mem_fraction_static if self.mem_fraction_static is not None else 0.85
         rest = free - total * (1 - frac)
@@ -126,10 +132,15 @@ class ModelRunner:
         ctx = self.server_args.context_length or cfg.context_len
         self.req_to_token_pool = ReqToTokenPool(size=max_num_reqs + 1, max_context_len=ctx + 4,
                                                 device=self.device)
-        self.token_to_kv_pool = MHATokenToKVPool(
-            self.max_total_num_tokens, page_size=1, dtype=self.kv_cache_dtype,
-            head_num=cfg.get_num_kv_heads(self.tp_size), head_dim=cfg.head_dim,
-            layer_num=cfg.num_hidden_layers, device=self.device)
+        if getattr(cfg, "model_type", "llama") == "deepseek_v2":
+            self.token_to_kv_pool = MLATokenToKVPool(
+                self.max_total_num_tokens, page_size=1, dtype=self.kv_cache_dtype, kv_lora_rank=cfg.kv_lora_rank,
+                qk_rope_head_dim=cfg.qk_rope_head_dim, layer_num=cfg.num_hidden_layers, device=self.device)
+        else:
+            self.token_to_kv_pool = MHATokenToKVPool(
+                self.max_total_num_tokens, page_size=1, dtype=self.kv_cache_dtype,
+                head_num=cfg.get_num_kv_heads(self.tp_size), head_dim=cfg.head_dim,
+                layer_num=cfg.num_hidden_layers, device=self.device)
         self.token_to_kv_pool_allocator = TokenToKVPoolAllocator(
             self.max_total_num_tokens, dtype=self.kv_cache_dtype, device=self.device,
             kvcache=self.token_to_kv_pool)

@@ -323,6 +323,125 @@ def linear(x: torch.Tensor, weight: torch.Tensor, out: Optional[torch.Tensor] = 
     return out
 
 
+def linear_block_diag(x: torch.Tensor, weight: torch.Tensor, num_groups: int, k: int, n: int,
+                      x_group_stride: int, out: Optional[torch.Tensor] = None,
+                      out_group_stride: int = 0) -> torch.Tensor:
+    """out[:, g*n:(g+1)*n] = x[:, g*x_group_stride : +k] @ weight[g*n:(g+1)*n, :k].T — the per-head
+    products of the absorbed MLA form (torch.bmm(q_nope, w_kc), torch.bmm(attn_out, w_vc)) as one launch."""
+    _cuda(x, weight)
+    if x.dim() != 2 or weight.dim() != 2 or x.stride(1) != 1 or weight.stride(1) != 1 or x.dtype != weight.dtype:
+        raise RuntimeError("linear_block_diag: x and weight must be 2-D, contiguous rows, same dtype")
+    M = x.shape[0]
+    if out is None:
+        out = torch.empty((M, num_groups * n), device=x.device, dtype=x.dtype)
+    check(lib.spd_gemm_grouped(out.data_ptr(), x.data_ptr(), weight.data_ptr(), M, n, k, x.stride(0),
+                               weight.stride(0), out.stride(0), num_groups, None, x_group_stride, x.shape[1],
+                               out_group_stride, 0, _dt(x), SPD_EPI_NONE, get_sm_budget(), _stream()),
+          "spd_gemm_grouped")
+    return out
+
+
+def linear_grouped_rows(x_sorted: torch.Tensor, weight: torch.Tensor, tile_group: torch.Tensor, num_groups: int,
+                        n: int, epilogue: int = SPD_EPI_NONE, k_concat: bool = False) -> torch.Tensor:
+    """Rows of x_sorted are grouped by expert in 128-row tiles; weight = the experts' [n (or 2n), K]
+    matrices stacked along the rows — or, k_concat, [n, E * K] concatenated along K.  → [rows, n]."""
+    _cuda(x_sorted, weight, tile_group)
+    M, K = x_sorted.shape
+    out = torch.empty((M, n), device=x_sorted.device, dtype=x_sorted.dtype)
+    check(lib.spd_gemm_grouped(out.data_ptr(), x_sorted.data_ptr(), weight.data_ptr(), M, n, K, x_sorted.stride(0),
+                               weight.stride(0), out.stride(0), num_groups, tile_group.data_ptr(), 0, K, 0,
+                               K if k_concat else 0, _dt(x_sorted), epilogue, get_sm_budget(), _stream()),
+          "spd_gemm_grouped")
+    return out
+
+
+def moe_route(logits: torch.Tensor, top_k: int, scale: float = 1.0, renormalize: bool = False):
+    """→ (topk_ids int32 [T, k], topk_weights fp32 [T, k])."""
+    _cuda(logits)
+    T, E = logits.shape
+    ids = torch.empty((T, top_k), device=logits.device, dtype=torch.int32)
+    w = torch.empty((T, top_k), device=logits.device, dtype=torch.float32)
+    check(lib.spd_moe_route(ids.data_ptr(), w.data_ptr(), logits.contiguous().data_ptr(), T, E, top_k, float(scale),
+                            1 if renormalize else 0, _dt(logits), _stream()), "spd_moe_route")
+    return ids, w
+
+
+def moe_align(topk_ids: torch.Tensor, num_experts: int):
+    """→ (row_token [R], inv_pos [T*k], tile_group [R/128]) with R = spd_moe_align_rows()."""
+    _cuda(topk_ids)
+    T, k = topk_ids.shape
+    R = lib.spd_moe_align_rows(T, k, num_experts)
+    dev = topk_ids.device
+    row_token = torch.empty((R,), device=dev, dtype=torch.int32)
+    inv_pos = torch.empty((T * k,), device=dev, dtype=torch.int32)
+    tile_group = torch.empty((R // 128,), device=dev, dtype=torch.int32)
+    check(lib.spd_moe_align(row_token.data_ptr(), inv_pos.data_ptr(), tile_group.data_ptr(), topk_ids.data_ptr(),
+                            T, k, num_experts, R, _stream()), "spd_moe_align")
+    return row_token, inv_pos, tile_group
+
+
+def moe_gather(x: torch.Tensor, row_token: torch.Tensor) -> torch.Tensor:
+    _cuda(x, row_token)
+    out = torch.empty((row_token.numel(), x.shape[1]), device=x.device, dtype=x.dtype)
+    check(lib.spd_moe_gather(out.data_ptr(), x.data_ptr(), row_token.data_ptr(), row_token.numel(), x.shape[1],
+                             x.stride(0), _dt(x), _stream()), "spd_moe_gather")
+    return out
+
+
+def moe_combine(y: torch.Tensor, inv_pos: torch.Tensor, topk_w: torch.Tensor,
+                shared: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(y, inv_pos, topk_w)
+    T, k = topk_w.shape
+    out = torch.empty((T, y.shape[1]), device=y.device, dtype=y.dtype)
+    check(lib.spd_moe_combine(out.data_ptr(), y.data_ptr(), shared.data_ptr() if shared is not None else None,
+                              inv_pos.data_ptr(), topk_w.data_ptr(), T, k, y.shape[1], _dt(y), _stream()),
+          "spd_moe_combine")
+    return out
+
+
+def moe_dense_act(gate_up: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Tensor, num_experts: int,
+                  inter: int) -> torch.Tensor:
+    _cuda(gate_up, topk_ids, topk_w)
+    T, k = topk_ids.shape
+    out = torch.empty((T, num_experts * inter), device=gate_up.device, dtype=gate_up.dtype)
+    check(lib.spd_moe_dense_act(out.data_ptr(), gate_up.data_ptr(), topk_ids.data_ptr(), topk_w.data_ptr(), T, k,
+                                num_experts, inter, _dt(gate_up), _stream()), "spd_moe_dense_act")
+    return out
+
+
+def kv_write_single(rows: torch.Tensor, pool: torch.Tensor, loc: torch.Tensor) -> None:
+    """pool[loc[t]] = rows[t] — MLATokenToKVPool.set_kv_buffer (one latent buffer per layer)."""
+    _cuda(rows, pool, loc)
+    T = rows.shape[0]
+    if T == 0:
+        return
+    r2 = rows.view(T, -1)
+    if loc.dtype != torch.int64:
+        loc = loc.long()
+    check(lib.spd_kv_write(r2.data_ptr(), None, pool.data_ptr(), None, loc.data_ptr(), T, r2.shape[1],
+                           r2.stride(0), 0, _dt(rows), _stream()), "spd_kv_write")
+
+
+def attn_mla(q: torch.Tensor, kv_pool: torch.Tensor, req_to_token, req_pool_indices, num_heads: int,
+             kv_lora_rank: int, rope_dim: int, sm_scale: float, workspace: torch.Tensor, seq_lens=None,
+             prefix_lens=None, extend_start_loc=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Absorbed MLA attention: decode (seq_lens) or ragged extend (prefix_lens + extend_start_loc).
+    q [T, H * (kv_lora + rope)] → out [T, H * kv_lora]."""
+    _cuda(q, kv_pool, req_to_token, req_pool_indices)
+    T = q.shape[0]
+    q2 = q.view(T, -1)
+    if out is None:
+        out = torch.empty((T, num_heads * kv_lora_rank), device=q.device, dtype=q.dtype)
+    check(lib.spd_attn_mla(out.data_ptr(), q2.data_ptr(), kv_pool.data_ptr(), req_to_token.data_ptr(),
+                           req_pool_indices.data_ptr(), seq_lens.data_ptr() if seq_lens is not None else None,
+                           prefix_lens.data_ptr() if prefix_lens is not None else None,
+                           extend_start_loc.data_ptr() if extend_start_loc is not None else None,
+                           req_pool_indices.numel(), T, num_heads, kv_lora_rank, rope_dim, q2.stride(0),
+                           out.stride(0), req_to_token.stride(0), float(sm_scale), _dt(q), workspace.data_ptr(),
+                           workspace.numel(), get_sm_budget(), _stream()), "spd_attn_mla")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------
