@@ -450,10 +450,10 @@ def compare_ids(got, want, margins, min_margin):
 # ----------------------------------------------------------------------------------------------
 # GPU stand-in baseline (flashinfer wrappers + cuBLAS), separate process
 # ----------------------------------------------------------------------------------------------
-def run_gpu_baseline(args, gpu):
+def run_gpu_baseline(args, gpu, rate=0.0):
     cmd = [sys.executable, os.path.join(ROOT, "scripts", "gpu_baseline_flashinfer.py"), "--gpu", str(gpu),
            "--requests", str(args.requests), "--input-len", str(args.input_len),
-           "--output-len", str(args.output_len), "--dtype", args.dtype, "--windows", "2"]
+           "--output-len", str(args.output_len), "--dtype", args.dtype, "--windows", "2", "--rate", str(rate)]
     try:
         p = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
         for line in reversed(p.stdout.strip().splitlines()):
@@ -757,7 +757,18 @@ def main():
             result["parity_check"] = {"error": repr(e)}
         del cpu_weights
     if rank == 0 and world == 1 and not args.no_gpu_baseline:
-        result["gpu_baseline"] = run_gpu_baseline(args, local_rank)
+        # same mix, same box, same run; its Poisson window runs at the rate of our `latency` block
+        gb = run_gpu_baseline(args, local_rank, result.get("latency", {}).get("request_rate", 0.0))
+        result["gpu_baseline"] = gb
+        if "output_tok_per_s" in gb:
+            cmp_ = {"output_tok_per_s": result["e2e"]["value"] / gb["output_tok_per_s"],
+                    "saturated_tpot_p50": gb["tpot_ms_p50"] / result["e2e"]["tpot_ms_p50"],
+                    "saturated_ttft_p50": gb["ttft_ms_p50"] / result["e2e"]["ttft_ms_p50"]}
+            if gb.get("latency") and result.get("latency"):
+                cmp_["at_rate_ttft_p50"] = gb["latency"]["ttft_ms_p50"] / result["latency"]["ttft_ms_p50"]
+                cmp_["at_rate_tpot_p50"] = gb["latency"]["tpot_ms_p50"] / result["latency"]["tpot_ms_p50"]
+            result["vs_gpu_baseline"] = {**cmp_, "note": "each > 1 means this build is better (throughput: ours / "
+                                                        "baseline; latencies: baseline / ours)"}
 
     if world > 1 and not args.no_tp:
         # The TP arm must never cost the replica numbers above: if a rank fails or the arm runs

@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--windows", type=int, default=2)
     ap.add_argument("--prefill-batch", type=int, default=8)
     ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--rate", type=float, default=0.0,
+                    help="also serve one Poisson window at this request rate (req/s) for TTFT / TPOT")
     ap.add_argument("--build-only", action="store_true", help="JIT-compile the flashinfer modules and exit (no GPU)")
     return ap.parse_args()
 
@@ -184,17 +186,27 @@ def main():
             graphs[bs] = g
     torch.cuda.synchronize()
 
-    def window():
+    def window(rate=0.0):
         lock = threading.Lock()
         ready = []           # (request index, first token tensor on device, done event)
         t_first, t_last = [0.0] * R, [0.0] * R
         n_tok = [0] * R
+        # arrivals: all at once (saturated) or exponential gaps as bench_serving.py:884-899
+        arr = [0.0] * R if rate <= 0 else np.cumsum(np.random.RandomState(1).exponential(1.0 / rate, size=R)).tolist()
         t0 = time.perf_counter()
 
         def prefill_loop():
             with torch.cuda.stream(p_stream):
-                for b0 in range(0, R, PB):
-                    idx = list(range(b0, min(b0 + PB, R)))
+                nxt = 0
+                while nxt < R:
+                    now = time.perf_counter() - t0
+                    if arr[nxt] > now:
+                        time.sleep(min(arr[nxt] - now, 0.002))
+                        continue
+                    idx = []
+                    while nxt < R and len(idx) < PB and arr[nxt] <= now:
+                        idx.append(nxt)
+                        nxt += 1
                     n = len(idx)
                     ids = prompts[idx].reshape(-1).to(dev, non_blocking=True)
                     pos = torch.arange(S_in, device=dev).repeat(n)
@@ -275,7 +287,7 @@ def main():
         td.join()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        ttft = [t - t0 for t in t_first]
+        ttft = [t_first[r] - t0 - arr[r] for r in range(R)]
         tpot = [(t_last[r] - t_first[r]) / (S_out - 1) for r in range(R)]
         return wall, ttft, tpot
 
@@ -287,11 +299,17 @@ def main():
         ttft += t1
         tpot += t2
     q = lambda x, p: float(np.percentile(np.array(x) * 1e3, p))  # noqa: E731
+    at_rate = None
+    if a.rate > 0:
+        w, t1, t2 = window(a.rate)
+        at_rate = {"request_rate": a.rate, "output_tok_per_s": R * S_out / w, "ttft_ms_p50": q(t1, 50),
+                   "ttft_ms_p99": q(t1, 99), "tpot_ms_p50": q(t2, 50), "tpot_ms_p99": q(t2, 99)}
     print(json.dumps({
         "kind": "flashinfer-" + flashinfer.__version__ + " wrappers + cuBLAS F.linear stand-in (NOT the reference build)",
         "output_tok_per_s": a.windows * R * S_out / sum(walls), "ms_per_window": 1e3 * sum(walls) / a.windows,
         "windows": a.windows, "requests": R, "input_len": S_in, "output_len": S_out, "layers": a.layers,
         "ttft_ms_p50": q(ttft, 50), "ttft_ms_p99": q(ttft, 99), "tpot_ms_p50": q(tpot, 50), "tpot_ms_p99": q(tpot, 99),
+        "latency": at_rate,
         "concurrency": "prefill and decode threads on two CUDA streams of one process (no MPS on the box), "
                        "decode stream at higher priority; CUDA-graph decode with a host plan() per step",
         "dtype": a.dtype}))
