@@ -779,7 +779,8 @@ def main():
                 print(json.dumps(result), flush=True)
             os._exit(0)
 
-        watchdog = threading.Timer(780.0, bail, args=("TP arm exceeded 780 s",))
+        tp_limit = 900.0 if world == 8 else 480.0
+        watchdog = threading.Timer(tp_limit, bail, args=(f"TP arm exceeded {tp_limit:.0f} s",))
         watchdog.daemon = True
         watchdog.start()
         try:

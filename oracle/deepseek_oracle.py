@@ -111,6 +111,7 @@ class DeepseekOracle:
         self.kv = [torch.zeros(kv_slots + 1, 1, L) for _ in range(cfg.num_hidden_layers)]
         self.req_to_token = torch.zeros(max_reqs, max_ctx, dtype=torch.int32)
         self.scaling = (cfg.qk_nope_head_dim + cfg.qk_rope_head_dim) ** -0.5
+        self.router_margins: List[torch.Tensor] = []
         self.inv_freq, self.rope_mag = rope_inv_freq(cfg.qk_rope_head_dim, cfg.rope_theta, cfg.rope_scaling)
         if cfg.rope_scaling:
             # models/deepseek_v2.py:504-509: softmax scale x mscale(factor, mscale_all_dim)^2
@@ -175,6 +176,11 @@ class DeepseekOracle:
         p = f"model.layers.{i}.mlp."
         probs = F.linear(x, w[p + "gate.weight"]).softmax(-1)
         topw, topi = probs.topk(cfg.num_experts_per_tok, dim=-1)
+        # test aid: how close every token's k-th and (k+1)-th expert are (a 16-bit implementation
+        # may legitimately pick the other one when this relative margin is below its rounding noise)
+        if probs.shape[-1] > cfg.num_experts_per_tok:
+            top = probs.topk(cfg.num_experts_per_tok + 1, dim=-1).values
+            self.router_margins.append(((top[:, -2] - top[:, -1]) / top[:, -2]).detach())
         out = torch.zeros_like(x)
         gu, dn = w[p + "experts.gate_up_proj"], w[p + "experts.down_proj"]  # [E, 2I, H], [E, H, I]
         I = cfg.moe_intermediate_size
@@ -189,6 +195,7 @@ class DeepseekOracle:
                 force_absorb=False):
         """Extend when extend_lens is given (last-token logits per request), else decode."""
         cfg, w = self.cfg, self.w
+        self.router_margins = []  # one [T] tensor per MoE layer of this forward (see _moe)
         h = F.embedding(input_ids, w["model.embed_tokens.weight"])
         for i in range(cfg.num_hidden_layers):
             p = f"model.layers.{i}."

@@ -77,7 +77,22 @@ struct PrefillParams {
   int batch;
   int total_items;
   int use_tma;  // 0: always gather (SPD_ATTN_TMA=0)
+  long long* trace;  // debug timeline of CTA 0 (scripts/debug_attn_prefill_timeline.py); kTrace builds only
+  int trace_cap;
 };
+
+// timeline region r: (tag, clock64) pairs written by one thread of CTA 0
+template <bool kTrace>
+__device__ __forceinline__ void pf_trace(const PrefillParams& p, int region, uint32_t& n, long long tag) {
+  if constexpr (kTrace) {
+    if (blockIdx.x == 0 && p.trace && static_cast<int>(n) < p.trace_cap) {
+      long long* e = p.trace + (static_cast<size_t>(region) * p.trace_cap + n) * 2;
+      e[0] = tag;
+      e[1] = clock64();
+      ++n;
+    }
+  }
+}
 
 struct PfItem {
   int req, pre, hk, n;         // n = KV tiles of the item (max over the two query tiles)
@@ -183,11 +198,12 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t* r, int c, uint32_t
   }
 }
 
-// One row of one S half for one thread: 64 columns of S (TMEM) -> 32 packed 16-bit pairs in
-// registers.  Returns the row sum of p (masked entries excluded).  The second TMEM load is in
-// flight while the first 32 columns are exponentiated.  kMask is a template parameter so that the
-// unmasked units run the lean loop: FFMA + MUFU.EX2 + FADD + half an F2FP per element.
-template <typename T, bool kMask>
+// One row of one S unit (kU = 64 or 128 columns) for one thread: S (TMEM) -> kU/2 packed 16-bit
+// pairs in registers.  Returns the row sum of p (masked entries excluded).  Two 32-column TMEM
+// loads are in flight while the previous 32 columns are exponentiated.  kMask is a template
+// parameter so that the unmasked units run the lean loop: FFMA + MUFU.EX2 + FADD + half an F2FP
+// per element.
+template <typename T, bool kMask, int kU>
 __device__ __forceinline__ float softmax_row_pass(uint32_t ts, uint32_t* pk, float scale_log2, float m_off,
                                                   int kv0, int limit) {
   const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
@@ -198,13 +214,20 @@ __device__ __forceinline__ float softmax_row_pass(uint32_t ts, uint32_t* pk, flo
   tmem_ld_32x32b_x32(ts + 32, rb);
   tmem_ld_wait();
   softmax_chunk<T, kMask>(ra, 0, pk, scale2, neg_m2, kv0, limit, ps);
+  if constexpr (kU == 128) tmem_ld_32x32b_x32(ts + 64, ra);  // in flight under the next chunk
   softmax_chunk<T, kMask>(rb, 32, pk + 16, scale2, neg_m2, kv0, limit, ps);
+  if constexpr (kU == 128) {
+    tmem_ld_32x32b_x32(ts + 96, rb);
+    tmem_ld_wait();
+    softmax_chunk<T, kMask>(ra, 64, pk + 32, scale2, neg_m2, kv0, limit, ps);
+    softmax_chunk<T, kMask>(rb, 96, pk + 48, scale2, neg_m2, kv0, limit, ps);
+  }
   float ps0, ps1;
   unpack_f32x2(ps, ps0, ps1);
   return ps0 + ps1;
 }
 
-// max of the visible raw scores of one row of an S half (TMEM)
+// max of the visible raw scores of one row of an S unit (TMEM)
 template <bool kMask>
 __device__ __forceinline__ void rowmax_chunk(const uint32_t* r, int c, int kv0, int limit, float& m0, float& m1) {
 #pragma unroll
@@ -218,19 +241,26 @@ __device__ __forceinline__ void rowmax_chunk(const uint32_t* r, int c, int kv0, 
     m1 = fmaxf(m1, b);
   }
 }
-template <bool kMask>
+template <bool kMask, int kU>
 __device__ __forceinline__ float softmax_row_max(uint32_t ts, int kv0, int limit) {
   float m0 = -INFINITY, m1 = -INFINITY;
-  uint32_t ra[32], rb[32];
-  tmem_ld_32x32b_x32(ts, ra);
-  tmem_ld_32x32b_x32(ts + 32, rb);
-  tmem_ld_wait();
-  rowmax_chunk<kMask>(ra, 0, kv0, limit, m0, m1);
-  rowmax_chunk<kMask>(rb, 32, kv0, limit, m0, m1);
+#pragma unroll
+  for (int c = 0; c < kU; c += 64) {
+    uint32_t ra[32], rb[32];
+    tmem_ld_32x32b_x32(ts + c, ra);
+    tmem_ld_32x32b_x32(ts + c + 32, rb);
+    tmem_ld_wait();
+    rowmax_chunk<kMask>(ra, c, kv0, limit, m0, m1);
+    rowmax_chunk<kMask>(rb, c + 32, kv0, limit, m0, m1);
+  }
   return fmaxf(m0, m1);
 }
 
-template <typename T>
+// kU: columns of one softmax / MMA unit.  64: the half-tile pipeline described above.  128: one
+// unit per K/V tile — S = Q K^T goes out as ONE N = 128 group (8 instead of 16 SS-form MMAs per
+// tile, the form whose fixed cost per instruction dominates at N = 64) and the two warpgroups
+// alternate on the tensor core tile by tile.
+template <typename T, int kU, bool kTrace>
 __global__ void __launch_bounds__(kPfThreads, 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const PrefillParams p) {
@@ -253,6 +283,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cta = blockIdx.x, ncta = gridDim.x;
+  constexpr int kNU = kPfN / kU;  // units per K/V tile
 
   if (warp == 10) {
     if (lane == 0) {
@@ -309,12 +340,13 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else if (warp == 10) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      constexpr uint32_t idesc_qk = umma_idesc<T>(kPfM, kPfH, 0, 0);  // A, B K-major; N = one half
+      constexpr uint32_t idesc_qk = umma_idesc<T>(kPfM, kU, 0, 0);  // A, B K-major; N = one unit
       constexpr uint32_t idesc_pv = umma_idesc<T>(kPfM, kPfD, 0, 1);  // A = P (TMEM), B = V MN-major
       uint32_t t_base = 0;          // tiles of all previous items (ring position / 2)
-      uint32_t pq[2] = {0, 0};      // PV units issued per warpgroup (all items); half = pq & 1
+      uint32_t pq[2] = {0, 0};      // PV units issued per warpgroup (all items); unit of the tile = pq % kNU
       uint32_t eq[2] = {0, 0};      // items per warpgroup (o_free phase)
       uint32_t itn = 0;
+      uint32_t tn = 0;
       for (int kk = 0;; ++kk) {
         const int idx = pf_rank(kk, cta, ncta);
         if (idx >= p.total_items) break;
@@ -322,31 +354,37 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (it.n == 0) continue;
         mbar_wait(q_full, itn & 1);
         // S_w(j, h): the warpgroup's previous P in these columns has been consumed by PV(j-1, h),
-        // issued earlier by this thread — tcgen05.mma executes in issue order
+        // issued earlier by this thread — tcgen05.mma executes in issue order.
+        // (Tried in round 2: interleaving the two warpgroups' MMAs instruction by instruction —
+        // back-to-back tcgen05.mma on ONE accumulator cost ~43 clk (SS) / ~10 clk (TS) more than
+        // N/2 each, alternating accumulators runs at the shared-memory operand rate,
+        // profiles/r02_tcgen05_2cta_probe.log.  The issuer's time per unit pair did drop from
+        // 2 x 795 to 1293 clk, but pairing forces both warpgroups' softmax passes into the same
+        // phase (1020 -> 1500 clk per pass, XU contention) and the kernel got 2-5 % slower.)
         auto issue_s = [&](int w, int j, int h) {
           const uint32_t pos = 2 * (t_base + j);
           mbar_wait(&kv_full[pos % kPfSlots], (pos / kPfSlots) & 1);
           tc_fence_after_sync();
           const uint32_t q_addr = smem_u32(sQ + w * kTileBytes);
-          const uint32_t k_addr = smem_u32(sKV + (pos % kPfSlots) * kTileBytes) + h * (kPfH * 128);
+          const uint32_t k_addr = smem_u32(sKV + (pos % kPfSlots) * kTileBytes) + h * (kU * 128);
 #pragma unroll
           for (int k = 0; k < kPfD / 16; ++k) {
             const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-            umma_ss(tmem_S + w * kPfN + h * kPfH, umma_desc_sw128(q_addr + off, 16, 1024),
+            umma_ss(tmem_S + w * kPfN + h * kU, umma_desc_sw128(q_addr + off, 16, 1024),
                     umma_desc_sw128(k_addr + off, 16, 1024), idesc_qk, k > 0 ? 1u : 0u);
           }
           umma_commit(&s_full[w * 2 + h]);
         };
-        // after both halves of S(j) of both warpgroups have been issued: release K_j, and Q after
+        // after every unit of S(j) of both warpgroups has been issued: release K_j, and Q after
         // the item's last S
         auto s_tile_issued = [&](int j) {
           umma_commit(&kv_empty[(2 * (t_base + j)) % kPfSlots]);
           if (j == it.n - 1) umma_commit(q_empty);
         };
         // the epilogue of the previous item reads O, not S — and its last PVs (reading P in the S
-        // columns) were issued before these, so S(0, a/b) may go out immediately
+        // columns) were issued before these, so S(0, .) may go out immediately
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < kNU; ++h)
 #pragma unroll
           for (int w = 0; w < 2; ++w)
             if (it.nt[w] > 0) issue_s(w, 0, h);
@@ -354,26 +392,29 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int j = 0; j < it.n; ++j) {
           const uint32_t vpos = 2 * (t_base + j) + 1;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < kNU; ++h) {
 #pragma unroll
             for (int w = 0; w < 2; ++w) {
               if (j >= it.nt[w]) continue;
-              mbar_wait(&p_full[w * 2 + h], (pq[w] >> 1) & 1);
+              pf_trace<kTrace>(p, 2, tn, 0x100 + w * 2 + h);  // waiting for P
+              mbar_wait(&p_full[w * 2 + h], (pq[w] / kNU) & 1);
+              pf_trace<kTrace>(p, 2, tn, 0x200 + w * 2 + h);  // P ready
               mbar_wait(&kv_full[vpos % kPfSlots], (vpos / kPfSlots) & 1);
               if (j == 0 && h == 0) mbar_wait(&o_free[w], (eq[w] & 1) ^ 1);  // previous item's O has been read
               tc_fence_after_sync();
-              const uint32_t v_addr = smem_u32(sKV + (vpos % kPfSlots) * kTileBytes) + h * (kPfH * 128);
+              const uint32_t v_addr = smem_u32(sKV + (vpos % kPfSlots) * kTileBytes) + h * (kU * 128);
 #pragma unroll
-              for (int k = 0; k < kPfH / 16; ++k) {
+              for (int k = 0; k < kU / 16; ++k) {
                 // A = P[128 x 16 kv]: 8 TMEM columns per k-step; B = V[16 kv x 128 d] (MN-major: 2
                 // blocks of 64 d, LBO = 16 KB; kv rows 128 B apart, 8-row groups SBO = 1 KB)
-                umma_ts(tmem_O + w * kPfD, tmem_S + w * kPfN + h * kPfH + k * 8,
+                umma_ts(tmem_O + w * kPfD, tmem_S + w * kPfN + h * kU + k * 8,
                         umma_desc_sw128(v_addr + k * 2048, 16384, 1024), idesc_pv,
                         (j > 0 || h > 0 || k > 0) ? 1u : 0u);
               }
               umma_commit(&pv_done[w * 2 + h]);
               ++pq[w];
               if (j + 1 < it.nt[w]) issue_s(w, j + 1, h);
+              pf_trace<kTrace>(p, 2, tn, 0x300 + w * 2 + h);  // PV (+ next S) issued
             }
           }
           umma_commit(&kv_empty[vpos % kPfSlots]);  // V_j: all PVs issued
@@ -482,7 +523,9 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t ts = tmem_S + lane_base + w * kPfN;
     const uint32_t to = tmem_O + lane_base + w * kPfD;
-    uint32_t u = 0;  // half-tile units processed by this warpgroup (all items); half = u & 1
+    uint32_t u = 0;  // units processed by this warpgroup (all items); unit of the tile = u % kNU
+    uint32_t tn = 0;
+    const bool tracer = kTrace && (threadIdx.x & 127) == 0;
     for (int k = 0;; ++k) {
       const int idx = pf_rank(k, cta, ncta);
       if (idx >= p.total_items) break;
@@ -496,38 +539,41 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int limit = it.pre + m0 + row;  // last visible key of this row (causal)
       float m_used = -INFINITY;  // max currently folded into O and l (raw score units)
       float l = 0.f;
-      for (int jh = 0; jh < 2 * nt; ++jh, ++u) {
-        const int h = jh & 1;
-        const int kv0 = (jh >> 1) * kPfN + h * kPfH;
-        const bool need_mask = (kv0 + kPfH - 1) > (it.pre + m0);
-        const uint32_t tsh = ts + h * kPfH;
-        mbar_wait(&s_full[w * 2 + h], (u >> 1) & 1);
+      for (int jh = 0; jh < kNU * nt; ++jh, ++u) {
+        const int h = jh % kNU;
+        const int kv0 = (jh / kNU) * kPfN + h * kU;
+        const bool need_mask = (kv0 + kU - 1) > (it.pre + m0);
+        const uint32_t tsh = ts + h * kU;
+        if (tracer) pf_trace<kTrace>(p, w, tn, 0x100 + h);  // waiting for S
+        mbar_wait(&s_full[w * 2 + h], (u / kNU) & 1);
         tc_fence_after_sync();
+        if (tracer) pf_trace<kTrace>(p, w, tn, 0x200 + h);  // S ready
         if (jh == 0) {
           // first unit of the item: establish the reference max with a max-only pre-pass
-          m_used = need_mask ? softmax_row_max<true>(tsh, kv0, limit) : softmax_row_max<false>(tsh, kv0, limit);
+          m_used = need_mask ? softmax_row_max<true, kU>(tsh, kv0, limit) : softmax_row_max<false, kU>(tsh, kv0, limit);
         }
         float m_off = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
-        uint32_t pk[32];
-        float psum = need_mask ? softmax_row_pass<T, true>(tsh, pk, p.scale_log2, m_off, kv0, limit)
-                               : softmax_row_pass<T, false>(tsh, pk, p.scale_log2, m_off, kv0, limit);
+        uint32_t pk[kU / 2];
+        float psum = need_mask ? softmax_row_pass<T, true, kU>(tsh, pk, p.scale_log2, m_off, kv0, limit)
+                               : softmax_row_pass<T, false, kU>(tsh, pk, p.scale_log2, m_off, kv0, limit);
         // raise the reference max only when some row may have outgrown it by > 2^8 (an element
         // above 2^8 implies a row sum above 2^8; warp-uniform decision: tcgen05.ld/st are
         // warp-collective); S is still intact (P is stored below), so the unit is simply redone
         if (__any_sync(0xffffffffu, psum > kRescaleTrigger)) {
-          const float mx = need_mask ? softmax_row_max<true>(tsh, kv0, limit) : softmax_row_max<false>(tsh, kv0, limit);
+          const float mx = need_mask ? softmax_row_max<true, kU>(tsh, kv0, limit)
+                                     : softmax_row_max<false, kU>(tsh, kv0, limit);
           const float m_new = fmaxf(m_used, mx);
           const float alpha = (m_used == -INFINITY) ? 0.f : fast_exp2((m_used - m_new) * p.scale_log2);
           l *= alpha;
           m_used = m_new;
           m_off = (m_used == -INFINITY) ? 0.f : m_used * p.scale_log2;
           if (jh > 0) {
-            // O must be quiescent: S of this unit was issued after PV of unit u-2 (so units <= u-2
-            // are complete), but PV of unit u-1 (the other half) may still be running.  pv_done
-            // is per half so that this wait cannot alias: on the other half's barrier at most
-            // the one phase we wait for is outstanding (a parity wait only tells the current
-            // phase from the one before it).
-            mbar_wait(&pv_done[w * 2 + ((u - 1) & 1)], ((u - 1) >> 1) & 1);
+            // O must be quiescent: S of this unit was issued after PV of unit u-kNU (so units
+            // <= u-kNU are complete), but PV of the units in between (the other half) may still
+            // be running.  pv_done is per unit-of-tile so that this wait cannot alias: on that
+            // barrier at most the one phase we wait for is outstanding (a parity wait only tells
+            // the current phase from the one before it).
+            mbar_wait(&pv_done[w * 2 + ((u - 1) % kNU)], ((u - 1) / kNU) & 1);
             tc_fence_after_sync();
 #pragma unroll 1
             for (int c = 0; c < kPfD; c += 32) {
@@ -539,22 +585,26 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               tmem_st_32x32b_x32(to + c, r);
             }
           }
-          psum = need_mask ? softmax_row_pass<T, true>(tsh, pk, p.scale_log2, m_off, kv0, limit)
-                           : softmax_row_pass<T, false>(tsh, pk, p.scale_log2, m_off, kv0, limit);
+          psum = need_mask ? softmax_row_pass<T, true, kU>(tsh, pk, p.scale_log2, m_off, kv0, limit)
+                           : softmax_row_pass<T, false, kU>(tsh, pk, p.scale_log2, m_off, kv0, limit);
         }
         l += psum;
-        // P over the first 32 columns of this S half (every column of it is in registers by now)
+        // P over the first kU/2 columns of this S unit (every column of it is in registers by now)
         tmem_st_32x32b_x32(tsh, pk);
+        if constexpr (kU == 128) tmem_st_32x32b_x32(tsh + 32, pk + 32);
         tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[w * 2 + h]);
+        if (tracer) pf_trace<kTrace>(p, w, tn, 0x300 + h);  // P published
       }
+      if (tracer) pf_trace<kTrace>(p, w, tn, 0x400);  // epilogue begins
       // ---- epilogue: O / l, TMEM -> registers -> global ----
       // last unit = half b of the last tile; S of that unit complete => PV(b) of the tile before is
       // complete, so only this one phase of pv_done[w][b] can be outstanding; PV(b) complete => PV(a)
-      mbar_wait(&pv_done[w * 2 + 1], ((u >> 1) - 1) & 1);
+      mbar_wait(&pv_done[w * 2 + (kNU - 1)], ((u - 1) / kNU) & 1);
       tc_fence_after_sync();
+      if (tracer) pf_trace<kTrace>(p, w, tn, 0x500);  // last PV complete
       const float inv_l = l > 0.f ? 1.f / l : 0.f;
       T* dst = reinterpret_cast<T*>(p.out) + static_cast<int64_t>(q_row0 + row) * p.out_stride +
                static_cast<int64_t>(head) * kPfD;
@@ -591,6 +641,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
       }
+      if (tracer) pf_trace<kTrace>(p, w, tn, 0x600);  // O stored
     }
   }
 
@@ -607,6 +658,16 @@ int check_attn_args(const char* fn, const void* out, const void* q, const void* 
 }  // namespace spd
 
 using namespace spd;
+
+// debug only (not part of include/spd.h): subsequent launches run the traced build and CTA 0 writes
+// its timeline — 3 regions (softmax warpgroup 0, 1, MMA issuer) of `cap` (tag, clock) pairs
+static long long* g_pf_trace = nullptr;
+static int g_pf_trace_cap = 0;
+extern "C" int spd_debug_attn_prefill_trace(void* buf, int64_t cap) {
+  g_pf_trace = static_cast<long long*>(buf);
+  g_pf_trace_cap = static_cast<int>(cap);
+  return 0;
+}
 
 extern "C" int spd_attn_prefill_ragged(void* out, const void* q, const void* k_pool,
                                        const void* v_pool, const int32_t* req_to_token,
@@ -661,14 +722,30 @@ extern "C" int spd_attn_prefill_ragged(void* out, const void* q, const void* k_p
   if ((rc = get_tmap(&tv, v_pool, 1ull << 31, row_elems, row_elems, kPfN))) return rc;
   const int sms = sm_budget > 0 ? sm_budget : device_sm_count_cached();
   const int grid = p.total_items < sms ? p.total_items : sms;
+  // SPD_ATTN_PF_UNIT = 64 | 128: width of a softmax / MMA unit (see the kernel's kU)
+  static const int unit = []() { const char* e = getenv("SPD_ATTN_PF_UNIT"); return (e && atoi(e) == 64) ? 64 : 128; }();
+#define SPD_PF_LAUNCH(U, TR)                                                                           \
+  do {                                                                                                 \
+    auto kern = attn_prefill_kernel<T, U, TR>;                                                         \
+    static bool configured = false;                                                                    \
+    if (!configured) {                                                                                 \
+      SPD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmem));      \
+      configured = true;                                                                               \
+    }                                                                                                  \
+    SPD_CUDA(launch(kern, dim3(grid), dim3(kPfThreads), kPfSmem, as_stream(stream), pdl_enabled(), tq, tk, tv, p)); \
+  } while (0)
   SPD_DISPATCH_DTYPE(dtype, {
-    auto kern = attn_prefill_kernel<T>;
-    static bool configured = false;
-    if (!configured) {
-      SPD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmem));
-      configured = true;
+    if (g_pf_trace) {
+      p.trace = g_pf_trace;
+      p.trace_cap = g_pf_trace_cap;
+      if (unit == 64) SPD_PF_LAUNCH(64, true);
+      else SPD_PF_LAUNCH(128, true);
+    } else if (unit == 64) {
+      SPD_PF_LAUNCH(64, false);
+    } else {
+      SPD_PF_LAUNCH(128, false);
     }
-    SPD_CUDA(launch(kern, dim3(grid), dim3(kPfThreads), kPfSmem, as_stream(stream), pdl_enabled(), tq, tk, tv, p));
   });
+#undef SPD_PF_LAUNCH
   return 0;
 }

@@ -293,7 +293,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
     auto store_chunk = [&](int xt, int yt, int c, const float* v) {
       if constexpr (!kSwap) {
         const int64_t m = static_cast<int64_t>(xt) * kBM + row;
-        int64_t n0 = static_cast<int64_t>(yt) * kBNOut + c;
+        const int64_t nl = static_cast<int64_t>(yt) * kBNOut + c;  // logical column: bounds; n0: where it lands
+        int64_t n0 = nl;
         if (p.c_group_cols > 0) {  // cols mode with strided output groups
           const int g = yt / p.y_tiles_per_group;
           n0 = g * p.c_group_cols + static_cast<int64_t>(yt - g * p.y_tiles_per_group) * kBNOut + c;
@@ -303,7 +304,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             float* dst = reinterpret_cast<float*>(p.C) + m * p.ldc + n0;
 #pragma unroll
             for (int j = 0; j < kChunk; j += 4) {
-              if (n0 + j < p.y_rows) {
+              if (nl + j < p.y_rows) {
                 float4 o;
                 o.x = to_f32<T>(from_f32<T>(v[j]));
                 o.y = to_f32<T>(from_f32<T>(v[j + 1]));
@@ -316,7 +317,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             T* dst = reinterpret_cast<T*>(p.C) + m * p.ldc + n0;
 #pragma unroll
             for (int j = 0; j < kChunk; j += 8) {
-              if (n0 + j < p.y_rows) {
+              if (nl + j < p.y_rows) {
                 uint4 o;
                 o.x = pack2<T>(v[j], v[j + 1]);
                 o.y = pack2<T>(v[j + 2], v[j + 3]);

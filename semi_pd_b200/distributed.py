@@ -9,7 +9,8 @@ CUDA-graph capture, of the [bs, vocab/tp] logits themselves as logits_processor.
 
 Dispatch (parallel_state.py:376-436 / custom_all_reduce.py:447-480): messages up to
 `SPD_AR_MAX_BYTES` (8 MiB) → `spd_allreduce` (one-shot / two-shot over IPC-mapped peer buffers,
-graph-capturable); larger ones → ncclAllReduce on the worker's own process group.
+graph-capturable); larger ones → the same kernel over slot-sized pieces (or, with SPD_TP_NCCL=1,
+ncclAllReduce on the worker's own process group).
 
 Under semi-PD the prefill and the decode worker of a GPU are two threads that share the model
 object, so the communicator cannot hang off the layers: each worker owns a `TpComm`
@@ -37,6 +38,9 @@ _tls = threading.local()
 
 SPD_AR_MAX_BYTES = int(os.environ.get("SPD_AR_MAX_BYTES", 8 << 20))
 _DT = {torch.bfloat16: 0, torch.float16: 1}
+# SPD_TP_NCCL=1: messages above SPD_AR_MAX_BYTES and the full-logits all-gather go through
+# torch.distributed's NCCL group instead of slot-sized pieces of the peer-memory kernels (A/B only)
+NCCL_FOR_LARGE = os.environ.get("SPD_TP_NCCL", "0") == "1"
 
 
 def init_distributed_environment(tp_size: int, tp_rank: int, backend: str = "nccl",
@@ -108,20 +112,44 @@ class TpComm:
     # ---- collectives ---------------------------------------------------------------------------
     def all_reduce(self, x: torch.Tensor, algo: int = 0) -> torch.Tensor:
         nbytes = x.numel() * x.element_size()
-        if (self._h is not None and x.dtype in _DT and nbytes <= self.max_bytes
-                and x.numel() % 8 == 0 and x.is_contiguous()):
+        spd_ok = (self._h is not None and x.dtype in _DT and x.numel() % 8 == 0 and x.is_contiguous())
+        if spd_ok and nbytes <= self.max_bytes:
             check(lib.spd_allreduce(self._h, x.data_ptr(), x.data_ptr(), x.numel(), _DT[x.dtype], algo,
                                     torch.cuda.current_stream().cuda_stream), "spd_allreduce")
+            return x
+        if spd_ok and not NCCL_FOR_LARGE:
+            # a large prefill batch: the same peer-memory kernel over slot-sized pieces (two-shot,
+            # stream-ordered) — no second communication library on the worker's stream
+            flat, step, st = x.view(-1), self.max_bytes // x.element_size(), torch.cuda.current_stream().cuda_stream
+            for off in range(0, flat.numel(), step):
+                n = min(step, flat.numel() - off)
+                ptr = flat.data_ptr() + off * x.element_size()
+                check(lib.spd_allreduce(self._h, ptr, ptr, n, _DT[x.dtype], algo, st), "spd_allreduce")
             return x
         dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
         return x
 
     def all_gather(self, x: torch.Tensor) -> torch.Tensor:
-        """[..., n] per rank → [..., tp * n] (last-dim concat, rank order)."""
+        """[rows, n] per rank → [rows, tp * n] (last-dim concat, rank order)."""
         inp = x.contiguous()
-        flat = torch.empty((self.world,) + tuple(inp.shape), dtype=inp.dtype, device=inp.device)
-        dist.all_gather_into_tensor(flat.view(self.world * inp.shape[0], *inp.shape[1:]), inp,
-                                    group=self.group)
+        rows = inp.shape[0]
+        row_bytes = (inp.numel() // max(rows, 1)) * inp.element_size()
+        if (self._h is not None and not NCCL_FOR_LARGE and rows > 0 and row_bytes % 16 == 0
+                and row_bytes <= self.max_bytes):
+            flat = torch.empty((self.world,) + tuple(inp.shape), dtype=inp.dtype, device=inp.device)
+            step, st = max(1, self.max_bytes // row_bytes), torch.cuda.current_stream().cuda_stream
+            for r0 in range(0, rows, step):
+                piece = inp[r0:r0 + step]
+                tmp = flat if step >= rows else torch.empty((self.world,) + tuple(piece.shape),
+                                                            dtype=inp.dtype, device=inp.device)
+                check(lib.spd_allgather(self._h, tmp.data_ptr(), piece.data_ptr(),
+                                        piece.numel() * inp.element_size(), st), "spd_allgather")
+                if tmp is not flat:
+                    flat[:, r0:r0 + step].copy_(tmp)
+        else:
+            flat = torch.empty((self.world,) + tuple(inp.shape), dtype=inp.dtype, device=inp.device)
+            dist.all_gather_into_tensor(flat.view(self.world * inp.shape[0], *inp.shape[1:]), inp,
+                                        group=self.group)
         return flat.movedim(0, -2).reshape(*x.shape[:-1], self.world * x.shape[-1])
 
     def all_gather_rows16(self, x: torch.Tensor) -> torch.Tensor:

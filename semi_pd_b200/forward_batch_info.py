@@ -76,6 +76,9 @@ class ModelWorkerBatch:
     # logprobs are unsupported under semi-PD (semi_pd_decode_scheduler.py:354)
     return_logprob: bool = False
     sampling_info: object = None
+    # TP > 1: all-gather the vocab-sharded logits (logits_processor.py:426-427).  The semi-PD
+    # schedulers sample greedy ids from the (max, argmax) rows and never read the logits.
+    gather_logits: bool = True
 
 
 @dataclasses.dataclass
@@ -99,6 +102,7 @@ class ForwardBatch:
     seq_lens_sum: int
 
     return_logprob: bool = False
+    gather_logits: bool = True
     positions: torch.Tensor = None
     decode_seq_lens_cpu: Optional[torch.Tensor] = None
 
@@ -130,6 +134,7 @@ class ForwardBatch:
             out_cache_loc=batch.out_cache_loc,
             seq_lens_sum=batch.seq_lens_sum,
             return_logprob=batch.return_logprob,
+            gather_logits=batch.gather_logits,
             sampling_info=batch.sampling_info,
             req_to_token_pool=model_runner.req_to_token_pool,
             token_to_kv_pool=model_runner.token_to_kv_pool,

@@ -249,7 +249,7 @@ class LogitsProcessor:
             valid = min(shard, max(self.config.vocab_size - get_tensor_model_parallel_rank() * shard, 1))
             pairs = ops.argmax_partial(logits[:, :valid], get_tensor_model_parallel_rank() * shard)
             next_ids = ops.argmax_merge(comm.all_gather_rows16(pairs))
-            if not torch.cuda.is_current_stream_capturing():
+            if forward_batch.gather_logits and not torch.cuda.is_current_stream_capturing():
                 logits = tensor_model_parallel_all_gather(logits)
         logits = logits[:, : self.config.vocab_size]
         return LogitsProcessorOutput(next_token_logits=logits, next_token_ids=next_ids)

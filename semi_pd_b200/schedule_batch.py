@@ -288,7 +288,8 @@ class ScheduleBatch:
             extend_num_tokens=self.extend_num_tokens if extend else None,
             extend_seq_lens=self.extend_lens if extend else None,
             extend_prefix_lens=self.prefix_lens if extend else None,
-            extend_logprob_start_lens=[0] * len(self.reqs) if extend else None)
+            extend_logprob_start_lens=[0] * len(self.reqs) if extend else None,
+            gather_logits=getattr(self, "gather_logits", True))
 
 
 def _cumsum(xs):

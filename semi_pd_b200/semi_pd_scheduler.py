@@ -205,6 +205,7 @@ class SemiPDPrefillScheduler(SemiPDScheduler):
         if resp.ready_event is not None:
             self.stream.wait_event(resp.ready_event)
         batch = self.to_extend_batch(resp)
+        batch.gather_logits = self.tp_size == 1  # only the greedy ids are consumed
         mwb = batch.get_model_worker_batch()
         _, next_token_ids = self.tp_worker.forward_batch_generation(mwb)
         self.forward_ct += 1
@@ -309,11 +310,12 @@ class SemiPDDecodeScheduler(SemiPDScheduler):
                                  m.sampling_params.ignore_eos, m.arrival_time))
                 elif isinstance(m, BatchProcessPrefillResultReq):
                     wire.append(("prefill_result",))
-            if self.stop_flag.is_set():
+            stopping = self.stop_flag.is_set()  # read ONCE: what is broadcast is what is acted on
+            if stopping:
                 wire.append(("stop",))
             box = [wire]
             dist.broadcast_object_list(box, src=0, group=self.cpu_group)
-            if self.stop_flag.is_set():
+            if stopping:
                 self._stop_broadcast = True
             for m in msgs:
                 self._dispatch(m)
@@ -520,6 +522,7 @@ class SemiPDDecodeScheduler(SemiPDScheduler):
         return None if self.running_batch.is_empty() else self.running_batch
 
     def run_batch(self, batch: ScheduleBatch):
+        batch.gather_logits = self.tp_size == 1
         mwb = batch.get_model_worker_batch()
         logits_output, next_token_ids = self.tp_worker.forward_batch_generation(mwb)
         self.forward_ct += 1
@@ -723,9 +726,12 @@ class SemiPDEngine:
                 raise RuntimeError(f"{s.role} scheduler died") from s.error
 
     def join(self, timeout: Optional[float] = None):
-        """TP ranks > 0: serve until rank 0's shutdown has been broadcast."""
-        for t in self.threads:
-            t.join(timeout=timeout)
+        """TP ranks > 0: serve until rank 0's shutdown has been broadcast.  The broadcast ends the
+        decode loop; the prefill loop of this rank has no other way to learn about it."""
+        self.threads[0].join(timeout=timeout)
+        if not self.threads[0].is_alive():
+            self.prefill.stop_flag.set()
+        self.threads[1].join(timeout=timeout)
 
     def shutdown(self):
         """Stop both loops and drop everything the engine owns on the device: CUDA graphs, the

@@ -125,9 +125,17 @@ def test_moe_route_and_align(ops, T, E, k):
     logits = torch.randn(T, E).bfloat16()
     ids, w = ops.moe_route(logits.to(DEV), k, scale=2.5)
     probs = logits.float().softmax(-1)
-    tw, ti = probs.topk(k, -1)
-    assert torch.equal(ids.cpu().long().sort(-1).values, ti.sort(-1).values)
-    assert torch.allclose(w.cpu().sort(-1).values, (tw * 2.5).sort(-1).values, rtol=1e-5, atol=1e-7)
+    # greedy top-k as the reference's topk_softmax kernel: repeated arg-max, ties -> the smaller
+    # expert id (16-bit logits DO tie; torch.topk leaves the order of ties unspecified)
+    rest, ti, tw = logits.float().clone(), [], []
+    for _ in range(k):
+        e = rest.argmax(-1)                      # first maximal index
+        ti.append(e)
+        tw.append(probs.gather(1, e[:, None])[:, 0])
+        rest.scatter_(1, e[:, None], -float("inf"))
+    ti, tw = torch.stack(ti, 1), torch.stack(tw, 1)
+    assert torch.equal(ids.cpu().long(), ti)
+    assert torch.allclose(w.cpu(), tw * 2.5, rtol=1e-5, atol=1e-7)
     _, wn = ops.moe_route(logits.to(DEV), k, scale=1.0, renormalize=True)
     assert torch.allclose(wn.cpu().sum(-1), torch.ones(T), atol=1e-5)
     row_token, inv_pos, tile_group = ops.moe_align(ids, E)
@@ -235,7 +243,7 @@ def _runner(rope_scaling, dtype, cuda_graph=False):
                        head_dim=192, rms_norm_eps=ocfg.rms_norm_eps, rope_theta=ocfg.rope_theta,
                        rope_scaling=rope_scaling, **MINI)
     sa = ServerArgs(model_path="mini-deepseek", dtype="float16" if dtype == torch.float16 else "bfloat16",
-                    load_format="external", max_total_tokens=8192, max_running_requests=16, context_length=2000,
+                    load_format="external", max_total_tokens=8192, max_running_requests=32, context_length=2000,
                     disable_cuda_graph=not cuda_graph, cuda_graph_bs=[1, 2, 4, 8] if cuda_graph else None,
                     enable_semi_pd=True)
     mr = ModelRunner(mcfg, 0.5, 0, 0, 1, 0, sa)
@@ -258,12 +266,31 @@ def test_deepseek_mini_model_matches_oracle(rope_scaling, dtype, tol):
     prompts = [[(7 + 13 * i + 31 * j) % V for i in range(n)] for j, n in enumerate(lens)]
     reqs, lg, ids = gs.extend(prompts)
     rids, lc = os_.extend(prompts)
-    assert (lg - lc).abs().max().item() < tol
+    # A request whose tokens include a router near-tie (relative margin between the k-th and the
+    # (k+1)-th expert below the 16-bit rounding noise of the hidden state) may legitimately
+    # route that token to the other expert: such rows get the loose bound, all others the tight
+    # one, and the loose ones must stay a minority.
+    noise = 4e-3 if dtype == torch.float16 else 3e-2
+    tight = torch.ones(len(lens), dtype=torch.bool)
+    if oracle.router_margins:
+        m = torch.stack(oracle.router_margins).min(0).values
+        ends = torch.tensor(lens).cumsum(0).tolist()
+        tight = torch.tensor([bool(m[e - n:e].min() > noise) for e, n in zip(ends, lens)])
+
+    def check(lg, lc):
+        err = (lg - lc).abs().max(-1).values
+        assert err[tight].max().item() < tol if tight.any() else True, err
+        assert err.max().item() < 6 * tol, err
+
+    check(lg, lc)
+    assert tight.sum() >= 3, tight
     tok = lc.argmax(-1).tolist()
     for _ in range(3):  # decode, bs = 5 (grouped path with few experts)
         lg, ids = gs.decode(reqs, tok)
         lc = os_.decode(rids, tok)
-        assert (lg - lc).abs().max().item() < tol
+        if oracle.router_margins:
+            tight &= torch.stack(oracle.router_margins).min(0).values > noise
+        check(lg, lc)
         tok = lc.argmax(-1).tolist()
     # chunked prefill: the second chunk attends to the cached latent prefix
     long = [(5 + 3 * i) % V for i in range(300)]
