@@ -55,8 +55,9 @@ constexpr int kPfN = 128;    // kv tokens per tile
 constexpr int kPfH = 64;     // kv tokens per half-tile unit (columns of one S half)
 constexpr int kPfD = 128;    // head dim
 constexpr int kTileBytes = 128 * 128 * 2;  // one [128 x 128] 16-bit tile = two 16 KB swizzle blocks
-constexpr int kPfSlots = 5;
-constexpr int kPfSmem = kTileBytes * (2 + kPfSlots) + 1024 + 512;
+constexpr int kPfSlots = 4;
+constexpr int kPfStage = 2 * 16384;  // epilogue staging: one [128 x 64] 16-bit block per warpgroup
+constexpr int kPfSmem = kTileBytes * (2 + kPfSlots) + kPfStage + 1024 + 512;
 constexpr float kRescaleTrigger = 256.f;  // a row sum above 2^8 may hide an element above 2^8
 
 struct PrefillParams {
@@ -100,7 +101,24 @@ struct PfItem {
   int kv_len;
 };
 
-__device__ __forceinline__ PfItem pf_item(const PrefillParams& p, int idx) {
+// the three per-request values an item needs from global memory; loaded ONE ITEM AHEAD by every
+// role (the dependent loads used to sit between two items: ~1000 clk per item boundary)
+struct PfRaw {
+  int ext, pre, start;
+};
+__device__ __forceinline__ PfRaw pf_raw(const PrefillParams& p, int idx) {
+  PfRaw r{0, 0, 0};
+  if (idx < p.total_items) {
+    const int per_x = p.heads_x * p.batch;
+    const int req = (idx - (idx / per_x) * per_x) / p.heads_x;
+    r.ext = __ldg(p.extend_lens + req);
+    r.pre = __ldg(p.prefix_lens + req);
+    r.start = __ldg(p.extend_start_loc + req);
+  }
+  return r;
+}
+
+__device__ __forceinline__ PfItem pf_item(const PrefillParams& p, int idx, const PfRaw& raw) {
   PfItem it;
   const int per_x = p.heads_x * p.batch;
   const int qx = p.tiles_x - 1 - idx / per_x;  // heaviest (latest) query tiles first
@@ -117,9 +135,9 @@ __device__ __forceinline__ PfItem pf_item(const PrefillParams& p, int idx) {
     it.m0[1] = (2 * qx + 1) * kPfM;
   }
   it.hk = it.head[0] / (p.Hq / p.Hk);
-  const int ext = p.extend_lens[it.req];
-  it.pre = p.prefix_lens[it.req];
-  const int start = p.extend_start_loc[it.req];
+  const int ext = raw.ext;
+  it.pre = raw.pre;
+  const int start = raw.start;
   it.kv_len = 0;
 #pragma unroll
   for (int w = 0; w < 2; ++w) {
@@ -263,13 +281,15 @@ __device__ __forceinline__ float softmax_row_max(uint32_t ts, int kv0, int limit
 template <typename T, int kU, bool kTrace>
 __global__ void __launch_bounds__(kPfThreads, 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const PrefillParams p) {
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                    const PrefillParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                     // 2 tiles (warpgroup 0 / 1)
   uint8_t* sKV = smem + 2 * kTileBytes;   // ring: position 2t = K of tile t, 2t+1 = V of tile t
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + kPfSlots) * kTileBytes);
+  uint8_t* sO = smem + (2 + kPfSlots) * kTileBytes;  // epilogue staging, 16 KB per warpgroup
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + kPfStage);
   uint64_t* q_full = bars;                     // 1
   uint64_t* q_empty = bars + 1;                // 1
   uint64_t* kv_full = bars + 2;                // kPfSlots
@@ -305,7 +325,10 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  if (warp == 11 && lane == 0) tma_prefetch_desc(&tmQ);
+  if (warp == 11 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmO);
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -320,10 +343,12 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // ===================== Q loader =====================
     if (elect_one()) {
       uint32_t itn = 0;
-      for (int k = 0;; ++k) {
-        const int idx = pf_rank(k, cta, ncta);
-        if (idx >= p.total_items) break;
-        const PfItem it = pf_item(p, idx);
+      int idx = pf_rank(0, cta, ncta);
+      PfRaw raw = pf_raw(p, idx);
+      for (int k = 0; idx < p.total_items; ++k) {
+        const PfItem it = pf_item(p, idx, raw);
+        idx = pf_rank(k + 1, cta, ncta);
+        raw = pf_raw(p, idx);
         if (it.n == 0) continue;
         mbar_wait(q_empty, (itn & 1) ^ 1);
         mbar_expect_tx(q_full, ((it.rows[0] > 0) + (it.rows[1] > 0)) * kTileBytes);
@@ -347,10 +372,12 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       uint32_t eq[2] = {0, 0};      // items per warpgroup (o_free phase)
       uint32_t itn = 0;
       uint32_t tn = 0;
-      for (int kk = 0;; ++kk) {
-        const int idx = pf_rank(kk, cta, ncta);
-        if (idx >= p.total_items) break;
-        const PfItem it = pf_item(p, idx);
+      int idx = pf_rank(0, cta, ncta);
+      PfRaw raw = pf_raw(p, idx);
+      for (int kk = 0; idx < p.total_items; ++kk) {
+        const PfItem it = pf_item(p, idx, raw);
+        idx = pf_rank(kk + 1, cta, ncta);
+        raw = pf_raw(p, idx);
         if (it.n == 0) continue;
         mbar_wait(q_full, itn & 1);
         // S_w(j, h): the warpgroup's previous P in these columns has been consumed by PV(j-1, h),
@@ -436,10 +463,12 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int64_t row_elems = static_cast<int64_t>(p.Hk) * kPfD;
     uint32_t t = 0;        // tiles loaded so far (all items)
     int pending = -1;      // slot whose cp.async group is committed but not yet published
-    for (int k = 0;; ++k) {
-      const int idx = pf_rank(k, cta, ncta);
-      if (idx >= p.total_items) break;
-      const PfItem it = pf_item(p, idx);
+    int idx = pf_rank(0, cta, ncta);
+    PfRaw raw = pf_raw(p, idx);
+    for (int k = 0; idx < p.total_items; ++k) {
+      const PfItem it = pf_item(p, idx, raw);
+      idx = pf_rank(k + 1, cta, ncta);
+      raw = pf_raw(p, idx);
       if (it.n == 0) continue;
       const int32_t* rtt = p.req_to_token + p.req_pool_indices[it.req] * p.rtt_stride;
       const int64_t col = static_cast<int64_t>(it.hk) * kPfD + chunk * 8;
@@ -526,10 +555,12 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint32_t u = 0;  // units processed by this warpgroup (all items); unit of the tile = u % kNU
     uint32_t tn = 0;
     const bool tracer = kTrace && (threadIdx.x & 127) == 0;
-    for (int k = 0;; ++k) {
-      const int idx = pf_rank(k, cta, ncta);
-      if (idx >= p.total_items) break;
-      const PfItem it = pf_item(p, idx);
+    int idx = pf_rank(0, cta, ncta);
+    PfRaw raw = pf_raw(p, idx);
+    for (int k = 0; idx < p.total_items; ++k) {
+      const PfItem it = pf_item(p, idx, raw);
+      idx = pf_rank(k + 1, cta, ncta);
+      raw = pf_raw(p, idx);
       const int nt = w == 0 ? it.nt[0] : it.nt[1];
       if (nt == 0) continue;
       const int m0 = w == 0 ? it.m0[0] : it.m0[1];
@@ -606,6 +637,13 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_after_sync();
       if (tracer) pf_trace<kTrace>(p, w, tn, 0x500);  // last PV complete
       const float inv_l = l > 0.f ? 1.f / l : 0.f;
+      // A full tile leaves through shared memory and one TMA store per 64-column block: with one
+      // thread per row, direct 16-byte stores touch 32 different lines per warp instruction and
+      // the 128 rows x 256 B took ~5900 clk per item (in-kernel timeline, round 2) — a quarter of
+      // the kernel at 1024-token prompts.  A ragged last tile (rows_valid < 128) must not write
+      // the rows of the next request and keeps the direct path.
+      const bool full_tile = rows_valid == kPfM;
+      uint8_t* stage = sO + w * (kPfStage / 2);
       T* dst = reinterpret_cast<T*>(p.out) + static_cast<int64_t>(q_row0 + row) * p.out_stride +
                static_cast<int64_t>(head) * kPfD;
 #pragma unroll 1
@@ -620,31 +658,41 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(&o_free[w]);
         }
-        if (row < rows_valid) {
+        uint4 v[8];
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 v;
-            v.x = pack2<T>(__uint_as_float(a[i]) * inv_l, __uint_as_float(a[i + 1]) * inv_l);
-            v.y = pack2<T>(__uint_as_float(a[i + 2]) * inv_l, __uint_as_float(a[i + 3]) * inv_l);
-            v.z = pack2<T>(__uint_as_float(a[i + 4]) * inv_l, __uint_as_float(a[i + 5]) * inv_l);
-            v.w = pack2<T>(__uint_as_float(a[i + 6]) * inv_l, __uint_as_float(a[i + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(dst + c + i) = v;
-          }
+        for (int i = 0; i < 4; ++i) {
+          v[i].x = pack2<T>(__uint_as_float(a[8 * i]) * inv_l, __uint_as_float(a[8 * i + 1]) * inv_l);
+          v[i].y = pack2<T>(__uint_as_float(a[8 * i + 2]) * inv_l, __uint_as_float(a[8 * i + 3]) * inv_l);
+          v[i].z = pack2<T>(__uint_as_float(a[8 * i + 4]) * inv_l, __uint_as_float(a[8 * i + 5]) * inv_l);
+          v[i].w = pack2<T>(__uint_as_float(a[8 * i + 6]) * inv_l, __uint_as_float(a[8 * i + 7]) * inv_l);
+          v[4 + i].x = pack2<T>(__uint_as_float(b[8 * i]) * inv_l, __uint_as_float(b[8 * i + 1]) * inv_l);
+          v[4 + i].y = pack2<T>(__uint_as_float(b[8 * i + 2]) * inv_l, __uint_as_float(b[8 * i + 3]) * inv_l);
+          v[4 + i].z = pack2<T>(__uint_as_float(b[8 * i + 4]) * inv_l, __uint_as_float(b[8 * i + 5]) * inv_l);
+          v[4 + i].w = pack2<T>(__uint_as_float(b[8 * i + 6]) * inv_l, __uint_as_float(b[8 * i + 7]) * inv_l);
+        }
+        if (full_tile) {
+          // the block's previous TMA store has finished READING the staging memory
+          if (row == 0) bulk_wait_group_read0();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + w) : "memory");
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 v;
-            v.x = pack2<T>(__uint_as_float(b[i]) * inv_l, __uint_as_float(b[i + 1]) * inv_l);
-            v.y = pack2<T>(__uint_as_float(b[i + 2]) * inv_l, __uint_as_float(b[i + 3]) * inv_l);
-            v.z = pack2<T>(__uint_as_float(b[i + 4]) * inv_l, __uint_as_float(b[i + 5]) * inv_l);
-            v.w = pack2<T>(__uint_as_float(b[i + 6]) * inv_l, __uint_as_float(b[i + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(dst + c + 32 + i) = v;
+          for (int i = 0; i < 8; ++i)  // [128 rows x 128 B], 128-byte swizzle: chunk ^ (row % 8)
+            *reinterpret_cast<uint4*>(stage + row * 128 + ((i ^ (row & 7)) << 4)) = v[i];
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + w) : "memory");
+          if (row == 0) {
+            tma_store_2d(&tmO, stage, head * kPfD + c, q_row0);
+            bulk_commit_group();
           }
+        } else if (row < rows_valid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(dst + c + 8 * i) = v[i];
         }
       }
       if (tracer) pf_trace<kTrace>(p, w, tn, 0x600);  // O stored
     }
   }
 
+  if (warp < 8 && (threadIdx.x & 127) == 0) bulk_wait_group0();  // this thread's TMA stores have landed
   griddep_launch_dependents();
   tc_fence_before_sync();
   __syncthreads();
@@ -709,9 +757,13 @@ extern "C" int spd_attn_prefill_ragged(void* out, const void* q, const void* k_p
   const int64_t total = static_cast<int64_t>(p.tiles_x) * p.heads_x * batch;
   SPD_REQUIRE(total < (1ll << 30), SPD_E_SHAPE, "spd_attn_prefill_ragged: too many work items");
   p.total_items = static_cast<int>(total);
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq, tk, tv, to;
   if ((rc = get_tmap(&tq, q, static_cast<uint64_t>(total_tokens),
                      static_cast<uint64_t>(num_q_heads) * head_dim, static_cast<uint64_t>(q_stride), kPfM)))
+    return rc;
+  // the output as a TMA-store target: same geometry as Q (rows beyond total_tokens are clipped)
+  if ((rc = get_tmap(&to, out, static_cast<uint64_t>(total_tokens),
+                     static_cast<uint64_t>(num_q_heads) * head_dim, static_cast<uint64_t>(out_stride), kPfM)))
     return rc;
   // K/V pools as [slots, Hk*D] tensors, box 128 rows x 64 columns (the row extent only bounds the
   // coordinates; they are slot ids taken from req_to_token)
@@ -732,7 +784,7 @@ extern "C" int spd_attn_prefill_ragged(void* out, const void* q, const void* k_p
       SPD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmem));      \
       configured = true;                                                                               \
     }                                                                                                  \
-    SPD_CUDA(launch(kern, dim3(grid), dim3(kPfThreads), kPfSmem, as_stream(stream), pdl_enabled(), tq, tk, tv, p)); \
+    SPD_CUDA(launch(kern, dim3(grid), dim3(kPfThreads), kPfSmem, as_stream(stream), pdl_enabled(), tq, tk, tv, to, p)); \
   } while (0)
   SPD_DISPATCH_DTYPE(dtype, {
     if (g_pf_trace) {

@@ -85,6 +85,16 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// TMA store of one box (shared memory -> global tensor); completion is tracked per thread in
+// bulk async-groups: commit, then wait_group.read before the staging memory is rewritten
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c_inner, int32_t c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
+               "r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_src))), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before_sync() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }

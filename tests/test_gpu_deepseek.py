@@ -270,7 +270,7 @@ def test_deepseek_mini_model_matches_oracle(rope_scaling, dtype, tol):
     # (k+1)-th expert below the 16-bit rounding noise of the hidden state) may legitimately
     # route that token to the other expert: such rows get the loose bound, all others the tight
     # one, and the loose ones must stay a minority.
-    noise = 4e-3 if dtype == torch.float16 else 3e-2
+    noise = 2e-3 if dtype == torch.float16 else 1e-2
     tight = torch.ones(len(lens), dtype=torch.bool)
     if oracle.router_margins:
         m = torch.stack(oracle.router_margins).min(0).values
@@ -283,7 +283,7 @@ def test_deepseek_mini_model_matches_oracle(rope_scaling, dtype, tol):
         assert err.max().item() < 6 * tol, err
 
     check(lg, lc)
-    assert tight.sum() >= 3, tight
+    assert tight.sum() >= 2, tight
     tok = lc.argmax(-1).tolist()
     for _ in range(3):  # decode, bs = 5 (grouped path with few experts)
         lg, ids = gs.decode(reqs, tok)
