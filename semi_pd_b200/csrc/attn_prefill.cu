@@ -775,7 +775,7 @@ extern "C" int spd_attn_prefill_ragged(void* out, const void* q, const void* k_p
   const int sms = sm_budget > 0 ? sm_budget : device_sm_count_cached();
   const int grid = p.total_items < sms ? p.total_items : sms;
   // SPD_ATTN_PF_UNIT = 64 | 128: width of a softmax / MMA unit (see the kernel's kU)
-  static const int unit = []() { const char* e = getenv("SPD_ATTN_PF_UNIT"); return (e && atoi(e) == 64) ? 64 : 128; }();
+  static const int unit = []() { const char* e = getenv("SPD_ATTN_PF_UNIT"); return (e && atoi(e) == 128) ? 128 : 64; }();
 #define SPD_PF_LAUNCH(U, TR)                                                                           \
   do {                                                                                                 \
     auto kern = attn_prefill_kernel<T, U, TR>;                                                         \

@@ -267,10 +267,12 @@ def test_deepseek_mini_model_matches_oracle(rope_scaling, dtype, tol):
     reqs, lg, ids = gs.extend(prompts)
     rids, lc = os_.extend(prompts)
     # A request whose tokens include a router near-tie (relative margin between the k-th and the
-    # (k+1)-th expert below the 16-bit rounding noise of the hidden state) may legitimately
+    # (k+1)-th expert below the rounding noise of the 16-bit router logits: the gate is a model-
+    # dtype linear in the reference too, deepseek_v2.py:128-139, so bf16 logits of magnitude ~2
+    # resolve 0.016 = 1.6 % of a probability) may legitimately
     # route that token to the other expert: such rows get the loose bound, all others the tight
     # one, and the loose ones must stay a minority.
-    noise = 2e-3 if dtype == torch.float16 else 1e-2
+    noise = 4e-3 if dtype == torch.float16 else 4e-2
     tight = torch.ones(len(lens), dtype=torch.bool)
     if oracle.router_margins:
         m = torch.stack(oracle.router_margins).min(0).values
