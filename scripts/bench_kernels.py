@@ -40,7 +40,9 @@ def graph_time(fns, reps=5):
 
 
 print(f"== decode-regime GEMMs (sm_budget={budget or 'all'}) ==")
-for M in ((1, 16, 64, 128, 160, 192) if "gd" in sections else ()):
+import os  # noqa: E402
+MS = tuple(int(x) for x in os.environ.get("SPD_BENCH_MS", "1,16,64,128,160,192").split(","))
+for M in (MS if "gd" in sections else ()):
     for (N, K, name) in ((6144, 4096, "qkv"), (4096, 4096, "o"), (28672, 4096, "gate_up"), (4096, 14336, "down"),
                          (128256, 4096, "lm_head")):
         nbuf = 3 if N > 100000 else 8

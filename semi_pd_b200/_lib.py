@@ -13,7 +13,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspd.so")
+# SPD_LIB_PATH: load another build of the same ABI (A/B runs of kernel changes on one box)
+LIB_PATH = os.environ.get("SPD_LIB_PATH") or os.path.join(_HERE, "libspd.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "spd.h")
 
 SPD_BF16 = 0

@@ -239,6 +239,11 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   fence_proxy_async_smem();
 
   // everything above overlaps the previous kernel's tail under PDL; seq_lens is its output
+  // PDL: release the dependents first (they block in their own griddepcontrol.wait until THIS grid
+  // has completed, and a grid completes only after its own wait — so order is transitive), then
+  // wait for the predecessor.  A decode GEMM two kernels downstream can then take over an SM the
+  // moment the previous GEMM's CTA leaves it and stream its weights under this kernel.
+  griddep_launch_dependents();
   griddep_wait();
   for (int i = threadIdx.x; i < min(p.batch, kDcLenCache); i += kDcThreads)
     s_len[i] = static_cast<int>(p.seq_lens[i]);
@@ -564,7 +569,6 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     }
   }
 
-  griddep_launch_dependents();
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem_base, 64);

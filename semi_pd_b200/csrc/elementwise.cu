@@ -65,6 +65,11 @@ rmsnorm_kernel(T* out, T* x, T* residual,  // out may alias x (fused variant is 
                const T* __restrict__ w, int64_t dim, int64_t x_stride, int64_t out_stride,
                float eps) {
   __shared__ float red[33];
+  // PDL: release the dependents first (they block in their own griddepcontrol.wait until THIS grid
+  // has completed, and a grid completes only after its own wait — so order is transitive), then
+  // wait for the predecessor.  A decode GEMM two kernels downstream can then take over an SM the
+  // moment the previous GEMM's CTA leaves it and stream its weights under this kernel.
+  griddep_launch_dependents();
   griddep_wait();
   const int64_t row = blockIdx.x;
   const int nvec = static_cast<int>(dim >> 3);
@@ -104,7 +109,6 @@ rmsnorm_kernel(T* out, T* x, T* residual,  // out may alias x (fused variant is 
   }
   const float total = block_sum(ss, red);
   const float inv = rsqrtf(total / static_cast<float>(dim) + eps);
-  griddep_launch_dependents();
   Vec8* orow = reinterpret_cast<Vec8*>(out + row * out_stride);
   const Vec8* wv = reinterpret_cast<const Vec8*>(w);
 #pragma unroll
@@ -137,6 +141,11 @@ rmsnorm_kernel(T* out, T* x, T* residual,  // out may alias x (fused variant is 
 template <typename T>
 __global__ void __launch_bounds__(256)
 silu_and_mul_kernel(T* __restrict__ out, const T* __restrict__ x, int64_t tokens, int64_t d) {
+  // PDL: release the dependents first (they block in their own griddepcontrol.wait until THIS grid
+  // has completed, and a grid completes only after its own wait — so order is transitive), then
+  // wait for the predecessor.  A decode GEMM two kernels downstream can then take over an SM the
+  // moment the previous GEMM's CTA leaves it and stream its weights under this kernel.
+  griddep_launch_dependents();
   griddep_wait();
   const int64_t nvec_row = d >> 3;
   const int64_t total = tokens * nvec_row;
@@ -151,7 +160,6 @@ silu_and_mul_kernel(T* __restrict__ out, const T* __restrict__ x, int64_t tokens
     for (int j = 0; j < 8; ++j) o[j] = g[j] / (1.0f + __expf(-g[j])) * u[j];
     reinterpret_cast<Vec8*>(out + t * d)[c] = f32_to_vec8<T>(o);
   }
-  griddep_launch_dependents();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -166,6 +174,11 @@ rope_kernel(T* __restrict__ q, T* __restrict__ k, const T* __restrict__ v, T* __
             T* __restrict__ v_pool, const float* __restrict__ cos_sin, const int64_t* __restrict__ pos_ids,
             const int64_t* __restrict__ loc, int Hq, int Hk, int D, int rot, int64_t q_stride,
             int64_t k_stride, int64_t v_stride, int interleave) {
+  // PDL: release the dependents first (they block in their own griddepcontrol.wait until THIS grid
+  // has completed, and a grid completes only after its own wait — so order is transitive), then
+  // wait for the predecessor.  A decode GEMM two kernels downstream can then take over an SM the
+  // moment the previous GEMM's CTA leaves it and stream its weights under this kernel.
+  griddep_launch_dependents();
   griddep_wait();
   const int64_t t = blockIdx.x;
   const int64_t pos = pos_ids[t];
@@ -251,7 +264,6 @@ rope_kernel(T* __restrict__ q, T* __restrict__ k, const T* __restrict__ v, T* __
     const Vec8* vsrc = reinterpret_cast<const Vec8*>(v + t * v_stride);
     for (int it = threadIdx.x; it < nv; it += blockDim.x) reinterpret_cast<Vec8*>(vdst)[it] = vsrc[it];
   }
-  griddep_launch_dependents();
 }
 
 template <typename T>
@@ -259,6 +271,11 @@ __global__ void __launch_bounds__(256)
 kv_write_kernel(const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ k_pool,
                 T* __restrict__ v_pool, const int64_t* __restrict__ loc, int64_t row_elems,
                 int64_t k_stride, int64_t v_stride) {
+  // PDL: release the dependents first (they block in their own griddepcontrol.wait until THIS grid
+  // has completed, and a grid completes only after its own wait — so order is transitive), then
+  // wait for the predecessor.  A decode GEMM two kernels downstream can then take over an SM the
+  // moment the previous GEMM's CTA leaves it and stream its weights under this kernel.
+  griddep_launch_dependents();
   griddep_wait();
   const int64_t t = blockIdx.x;
   const int64_t slot = loc[t];
@@ -275,13 +292,17 @@ kv_write_kernel(const T* __restrict__ k, const T* __restrict__ v, T* __restrict_
       vd[i] = vs[i];
     }
   }
-  griddep_launch_dependents();
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(T* __restrict__ out, const T* __restrict__ table, const int64_t* __restrict__ idx,
                    int64_t row_elems, int64_t table_rows) {
+  // PDL: release the dependents first (they block in their own griddepcontrol.wait until THIS grid
+  // has completed, and a grid completes only after its own wait — so order is transitive), then
+  // wait for the predecessor.  A decode GEMM two kernels downstream can then take over an SM the
+  // moment the previous GEMM's CTA leaves it and stream its weights under this kernel.
+  griddep_launch_dependents();
   griddep_wait();
   const int64_t i = blockIdx.x;
   const int64_t r = idx[i];
@@ -294,7 +315,6 @@ gather_rows_kernel(T* __restrict__ out, const T* __restrict__ table, const int64
     const Vec8* s = reinterpret_cast<const Vec8*>(table + r * row_elems);
     for (int c = threadIdx.x; c < nv; c += blockDim.x) d[c] = s[c];
   }
-  griddep_launch_dependents();
 }
 
 // argmax over fp32 rows; ties resolve to the smallest index (torch.argmax on CUDA/CPU returns the
@@ -305,6 +325,11 @@ argmax_kernel(int32_t* __restrict__ ids, const float* __restrict__ logits, int64
               int4* __restrict__ pairs, int idx_offset) {
   __shared__ float sv[32];
   __shared__ int si[32];
+  // PDL: release the dependents first (they block in their own griddepcontrol.wait until THIS grid
+  // has completed, and a grid completes only after its own wait — so order is transitive), then
+  // wait for the predecessor.  A decode GEMM two kernels downstream can then take over an SM the
+  // moment the previous GEMM's CTA leaves it and stream its weights under this kernel.
+  griddep_launch_dependents();
   griddep_wait();
   const float* row = logits + blockIdx.x * ld;
   float best = -INFINITY;
@@ -348,13 +373,17 @@ argmax_kernel(int32_t* __restrict__ ids, const float* __restrict__ logits, int64
       if (pairs) pairs[blockIdx.x] = make_int4(__float_as_int(best), bi + idx_offset, 0, 0);
     }
   }
-  griddep_launch_dependents();
 }
 
 // ids[b] = index of the largest of `parts` (max, index) candidates per row; ties resolve to the
 // smallest index, so the result equals torch.argmax over the concatenated shards.
 __global__ void argmax_merge_kernel(int32_t* __restrict__ ids, const int4* __restrict__ pairs, int parts,
                                     int64_t batch) {
+  // PDL: release the dependents first (they block in their own griddepcontrol.wait until THIS grid
+  // has completed, and a grid completes only after its own wait — so order is transitive), then
+  // wait for the predecessor.  A decode GEMM two kernels downstream can then take over an SM the
+  // moment the previous GEMM's CTA leaves it and stream its weights under this kernel.
+  griddep_launch_dependents();
   griddep_wait();
   const int64_t b = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (b >= batch) return;
@@ -403,13 +432,17 @@ compute_positions_kernel(int64_t* __restrict__ positions, int32_t* __restrict__ 
 
 __global__ void decode_positions_kernel(int64_t* __restrict__ positions,
                                         const int64_t* __restrict__ seq_lens, int64_t batch) {
+  // PDL: release the dependents first (they block in their own griddepcontrol.wait until THIS grid
+  // has completed, and a grid completes only after its own wait — so order is transitive), then
+  // wait for the predecessor.  A decode GEMM two kernels downstream can then take over an SM the
+  // moment the previous GEMM's CTA leaves it and stream its weights under this kernel.
+  griddep_launch_dependents();
   griddep_wait();
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i < batch) {
     const int64_t p = seq_lens[i] - 1;
     positions[i] = p < 0 ? 0 : p;
   }
-  griddep_launch_dependents();
 }
 
 __global__ void __launch_bounds__(256)
@@ -462,6 +495,11 @@ __global__ void __launch_bounds__(kNormThreads)
 layernorm_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ gamma,
                  const T* __restrict__ beta, int64_t dim, int64_t x_stride, int64_t out_stride, float eps) {
   __shared__ float red[33];
+  // PDL: release the dependents first (they block in their own griddepcontrol.wait until THIS grid
+  // has completed, and a grid completes only after its own wait — so order is transitive), then
+  // wait for the predecessor.  A decode GEMM two kernels downstream can then take over an SM the
+  // moment the previous GEMM's CTA leaves it and stream its weights under this kernel.
+  griddep_launch_dependents();
   griddep_wait();
   const int64_t row = blockIdx.x;
   const int nvec = static_cast<int>(dim >> 3);
@@ -492,7 +530,6 @@ layernorm_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restri
   }
   __syncthreads();  // `red` is reused
   const float inv = rsqrtf(block_sum(ss, red) / static_cast<float>(dim) + eps);
-  griddep_launch_dependents();
   Vec8* orow = reinterpret_cast<Vec8*>(out + row * out_stride);
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) {
@@ -512,6 +549,11 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bias_act_residual_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ bias,
                          const T* __restrict__ residual, int64_t tokens, int64_t dim, int act) {
+  // PDL: release the dependents first (they block in their own griddepcontrol.wait until THIS grid
+  // has completed, and a grid completes only after its own wait — so order is transitive), then
+  // wait for the predecessor.  A decode GEMM two kernels downstream can then take over an SM the
+  // moment the previous GEMM's CTA leaves it and stream its weights under this kernel.
+  griddep_launch_dependents();
   griddep_wait();
   const int64_t nvec_row = dim >> 3;
   const int64_t total = tokens * nvec_row;
@@ -538,7 +580,6 @@ bias_act_residual_kernel(T* __restrict__ out, const T* __restrict__ x, const T* 
     }
     reinterpret_cast<Vec8*>(out)[i] = f32_to_vec8<T>(f);
   }
-  griddep_launch_dependents();
 }
 
 }  // namespace spd

@@ -211,8 +211,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  // everything above overlaps the previous kernel's tail under PDL
-  griddep_wait();
+  // everything above overlaps the previous kernel's tail under PDL.  In the decode regime
+  // (swap-AB: X = the weights) the producer also fills the ring with WEIGHT tiles before it waits
+  // for the predecessor — see gemm_pair_decode.cu — and the dependents are released at once.
+  if constexpr (kSwap) griddep_launch_dependents();
+  if (!(kSwap && warp == 0)) griddep_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -220,6 +223,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       const uint64_t polX = kSwap ? kEvictFirst : kEvictNormal;
       const uint64_t polY = kSwap ? kEvictLast : kEvictNormal;
       int stage = 0, phase = 0;
+      int ahead = 0;
+      if constexpr (kSwap) {
+        SegIter pre;
+        pre.init(p);
+        int tile, kb0, kb1, slot;
+        while (ahead < kStages && pre.next(tile, kb0, kb1, slot)) {
+          int xt, yt;
+          tile_coords(p, tile, xt, yt);
+          for (int kb = kb0; kb < kb1 && ahead < kStages; ++kb, ++ahead) {
+            mbar_expect_tx(&full[ahead], kXBytes + kYBytes);
+            tma_load_2d(sX + ahead * kXBytes, &tmX, &full[ahead], kb * kBK, xt * kBM, polX);
+          }
+        }
+        griddep_wait();
+      }
+      int n = 0;
       SegIter it;
       it.init(p);
       int tile, kb0, kb1, slot;
@@ -227,7 +246,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
         int xt, yt, xcol0, yrow0, ycol0;
         tile_coords(p, tile, xt, yt);
         if (!group_offsets(p, xt, yt, xcol0, yrow0, ycol0)) continue;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb, ++n) {
+          if (n < ahead) {  // the weight tile of this stage is already in flight (or landed)
+            tma_load_2d(sY + stage * kYBytes, &tmY, &full[stage], ycol0 + kb * kBK, yrow0 + yt * BN, polY);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], kXBytes + kYBytes);
           tma_load_2d(sX + stage * kXBytes, &tmX, &full[stage], xcol0 + kb * kBK, xt * kBM, polX);
@@ -489,7 +513,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
     }
   }
 
-  griddep_launch_dependents();
+  if constexpr (!kSwap) griddep_launch_dependents();
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
@@ -653,6 +677,13 @@ int spd_gemm(void* C, const void* A, const void* W, int64_t M, int64_t N, int64_
   // rows (the un-swapped form would pad 160 tokens to 2 x 128 and read W twice from L2).
   const bool swap = (M <= env_swapmax) && epilogue == SPD_EPI_NONE;
   if (swap) {
+    // experiment knob: SPD_GEMM_PREFER_CLUSTER=1 routes few-tile layers at M <= 128 to the DSMEM
+    // split-K kernel before the pair kernel is considered
+    static const int env_prefer_cluster = getenv("SPD_GEMM_PREFER_CLUSTER") ? atoi(getenv("SPD_GEMM_PREFER_CLUSTER")) : 0;
+    if (env_prefer_cluster && M > 32 && (N + kBM - 1) / kBM <= sms / 2) {
+      rc = gemm_cluster_try(C, A, W, M, N, K, lda, ldw, ldc, dtype, out_f32, sms, st);
+      if (rc != 1) return rc;
+    }
     // 32 < M <= 256: CTA pairs share one activation tile between 256 weight rows (gemm_pair_decode.cu)
     rc = gemm_pair_decode_try(C, A, W, M, N, K, lda, ldw, ldc, dtype, out_f32, sms, ws_ok ? p.ws : nullptr,
                               kGemmWsBytes, ws_ok ? p.counters : nullptr, kGemmCounters, env_split, st);

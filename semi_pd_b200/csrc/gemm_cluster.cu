@@ -104,15 +104,26 @@ gemm_cluster_splitk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid
   cluster_sync_all();  // every CTA's barriers are initialised before any remote arrive
   const uint32_t tmem_base = *tmem_slot;
 
-  griddep_wait();
+  // PDL at both ends (see gemm_pair_decode.cu): dependents are released at once, and the ring is
+  // filled with weight tiles before this grid waits for its predecessor
+  griddep_launch_dependents();
+  if (warp != 0) griddep_wait();
 
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0, phase = 0;
+      int ahead = 0;
+      for (int kb = kb0; kb < kb1 && ahead < kStages; ++kb, ++ahead) {
+        mbar_expect_tx(&full[ahead], kXBytes + kYBytes);
+        tma_load_2d(sX + ahead * kXBytes, &tmW, &full[ahead], kb * kCgBK, tile * kCgBM, kEvictFirst);
+      }
+      griddep_wait();
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], kXBytes + kYBytes);
-        tma_load_2d(sX + stage * kXBytes, &tmW, &full[stage], kb * kCgBK, tile * kCgBM, kEvictFirst);
+        if (kb - kb0 >= ahead) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], kXBytes + kYBytes);
+          tma_load_2d(sX + stage * kXBytes, &tmW, &full[stage], kb * kCgBK, tile * kCgBM, kEvictFirst);
+        }
         tma_load_2d(sY + stage * kYBytes, &tmA, &full[stage], kb * kCgBK, 0, kEvictLast);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -195,7 +206,6 @@ gemm_cluster_splitk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid
     }
   }
 
-  griddep_launch_dependents();
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();  // nobody leaves while a peer may still touch its shared memory / barriers

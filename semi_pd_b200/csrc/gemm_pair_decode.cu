@@ -200,23 +200,49 @@ gemm_pair_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_co
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  griddep_wait();
+  // Programmatic dependent launch, both ends.  The dependents of this grid may be scheduled as
+  // soon as every CTA is running (they block in their own griddepcontrol.wait until this grid has
+  // completed); and this grid was itself launched while its predecessor was still running: the
+  // WEIGHTS do not depend on the predecessor, so the producer fills the whole TMA ring with
+  // weight tiles BEFORE it waits — a decode GEMM that follows RMSNorm / RoPE / SiLU·mul / the
+  // attention streams its first ~200 KB per SM (x 148 = 29 MB: all of W_o, 60 % of W_qkv) in the
+  // shadow of that kernel.  Only the activation tiles and every global write wait.
+  griddep_launch_dependents();
 
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0, phase = 0;
+      const int a_row = static_cast<int>(rank) * (BN / 2);
+      // pass 0: weights of the first kStages k-blocks (no predecessor data); then wait; pass 1:
+      // their activation tiles, and everything after them as usual
+      int ahead = 0;
+      {
+        PdSegIter it;
+        it.init(p, pair, npairs);
+        int tile, kb0, kb1;
+        while (ahead < kStages && it.next(tile, kb0, kb1)) {
+          const int w_row = tile * (2 * kPdBM) + static_cast<int>(rank) * kPdBM;
+          for (int kb = kb0; kb < kb1 && ahead < kStages; ++kb, ++ahead) {
+            if (rank == 0) mbar_expect_tx(&full[ahead], 2 * (kPdWBytes + kABytes));
+            pd_tma_load(sW + ahead * kPdWBytes, &tmW, map_to_rank(smem_u32(&full[ahead]), 0), kb * kPdBK, w_row,
+                        kEvictFirst);
+          }
+        }
+      }
+      griddep_wait();
       PdSegIter it;
       it.init(p, pair, npairs);
-      int tile, kb0, kb1;
+      int tile, kb0, kb1, n = 0;
       while (it.next(tile, kb0, kb1)) {
         const int w_row = tile * (2 * kPdBM) + static_cast<int>(rank) * kPdBM;
-        const int a_row = static_cast<int>(rank) * (BN / 2);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          if (rank == 0) mbar_expect_tx(&full[stage], 2 * (kPdWBytes + kABytes));
+        for (int kb = kb0; kb < kb1; ++kb, ++n) {
           const uint32_t lead_full = map_to_rank(smem_u32(&full[stage]), 0);
-          // weights stream through once; the activations are re-read by every pair
-          pd_tma_load(sW + stage * kPdWBytes, &tmW, lead_full, kb * kPdBK, w_row, kEvictFirst);
+          if (n >= ahead) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * (kPdWBytes + kABytes));
+            // weights stream through once; the activations are re-read by every pair
+            pd_tma_load(sW + stage * kPdWBytes, &tmW, lead_full, kb * kPdBK, w_row, kEvictFirst);
+          }
           pd_tma_load(sA + stage * kABytes, &tmA, lead_full, kb * kPdBK, a_row, kEvictLast);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -254,6 +280,7 @@ gemm_pair_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_co
       }
     }
   } else if (warp >= 4) {
+    griddep_wait();  // C, the split-K workspace and its flags are global memory
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 128;
@@ -442,7 +469,6 @@ gemm_pair_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_co
     PD_STAMP(6);  // epilogue role done
   }
 
-  griddep_launch_dependents();
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();  // the peer may still read this CTA's shared memory / signal its barriers
