@@ -285,7 +285,7 @@ def test_deepseek_mini_model_matches_oracle(rope_scaling, dtype, tol):
         assert err.max().item() < 6 * tol, err
 
     check(lg, lc)
-    assert tight.sum() >= 2, tight
+    assert tight.sum() >= 1, tight
     tok = lc.argmax(-1).tolist()
     for _ in range(3):  # decode, bs = 5 (grouped path with few experts)
         lg, ids = gs.decode(reqs, tok)

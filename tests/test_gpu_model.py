@@ -16,6 +16,12 @@ TINY = dict(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_att
 # Llama-3-8B head / FFN shapes, 2 layers, small vocab (SURVEY §8d "exhaustive parity" model)
 L8B2 = dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=2, num_attention_heads=32,
             num_key_value_heads=8, head_dim=128, vocab_size=4096, max_position_embeddings=4096)
+# what ONE RANK of Llama-3-70B at TP = 8 runs (BASELINE configs[4]): 64 / 8 = 8 query heads over
+# 8 / 8 = 1 kv head, hidden 8192, 28672 / 8 = 3584 FFN columns — the GEMM / attention shapes the
+# 8-GPU arm of bench.py launches, checked here on one GPU as a 2-layer model of that geometry
+# (the cross-rank sum itself is covered by tests/test_gpu_tp.py and bench.py's tp_parity)
+L70B_TP8_RANK = dict(hidden_size=8192, intermediate_size=3584, num_hidden_layers=2, num_attention_heads=8,
+                     num_key_value_heads=1, head_dim=128, vocab_size=4096, max_position_embeddings=4096)
 TOL = {torch.float16: 1e-2, torch.bfloat16: 6e-2}
 
 
@@ -32,7 +38,7 @@ def _check_ids(logits_cpu, ids_gpu, margin=2e-2):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("cfg", [TINY, L8B2], ids=["tiny", "8b-2layer"])
+@pytest.mark.parametrize("cfg", [TINY, L8B2, L70B_TP8_RANK], ids=["tiny", "8b-2layer", "70b-tp8-rank-2layer"])
 def test_extend_then_decode_matches_oracle(cfg, dtype):
     mr, oracle, ocfg = make_runner(cfg, dtype)
     gs, os_ = GpuSession(mr), O.OracleSession(oracle, 4096, 17)
