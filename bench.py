@@ -561,7 +561,7 @@ def tp_arm(args, model_name, rank, world, local_rank, dtype, requests, steps, ta
                "ar_timeouts": engine.d_worker.model_runner.tp_comm.status() + engine.p_worker.model_runner.tp_comm.status(),
                "sm_partition": {"prefill_sms": engine.p_sms, "decode_sms": engine.d_sms}, "setup_s": setup,
                "collectives": "spd_allreduce (peer memory over NVLink, one-/two-shot, graph-captured in decode); "
-                              "messages > 8 MiB (prefill batches) go through the same kernel in slot-sized "
+                              "messages > 32 MiB (prefill batches) go through the same kernel in slot-sized "
                               "pieces; (max, argmax) spd_allgather for the vocab-sharded lm_head; no NCCL "
                               "call on the serving path",
                "timing": "host wall clock on rank 0 around submit .. last token (all ranks run in lockstep)"}

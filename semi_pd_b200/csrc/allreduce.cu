@@ -118,6 +118,57 @@ __device__ __forceinline__ int4 pack8(const float (&acc)[8]) {
   return v;
 }
 
+// out[i] (and res[i] if given) = sum over ranks of slot_r[i], i in [lo, hi), rank order, fp32.
+// U vectors per thread are loaded from every rank before any is consumed: with one 16-byte load
+// in flight per thread a block pulls ~8 KB per NVLink round trip (~3 us) — 32 blocks then move
+// < 100 GB/s, which made a 64 MiB prefill all-reduce cost as much as the layer it follows.
+template <typename T, int W, int U>
+__device__ __forceinline__ void reduce_span(const ArParams& p, int world, int64_t slot_off, int64_t lo, int64_t hi,
+                                            int4* out, int4* res) {
+  for (int64_t i0 = lo + threadIdx.x; i0 < hi; i0 += static_cast<int64_t>(kArThreads) * U) {
+    int4 v[U][kArMaxRanks];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + static_cast<int64_t>(u) * kArThreads;
+      if (i < hi) {
+#pragma unroll
+        for (int r = 0; r < kArMaxRanks; ++r)
+          if (r < world) v[u][r] = __ldcv(reinterpret_cast<const int4*>(p.peers.base[r] + slot_off) + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + static_cast<int64_t>(u) * kArThreads;
+      if (i < hi) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < kArMaxRanks; ++r)
+          if (r < world) accum8<T>(acc, v[u][r]);
+        const int4 o = pack8<T>(acc);
+        if (res) res[i] = o;
+        out[i] = o;
+      }
+    }
+  }
+}
+
+// dst[i] = src[i], i in [lo, hi), four 16-byte loads per thread in flight (src may be peer memory)
+__device__ __forceinline__ void copy_span(int4* dst, const int4* src, int64_t lo, int64_t hi, bool peer) {
+  for (int64_t i0 = lo + threadIdx.x; i0 < hi; i0 += static_cast<int64_t>(kArThreads) * 4) {
+    int4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + static_cast<int64_t>(u) * kArThreads;
+      if (i < hi) v[u] = peer ? __ldcv(src + i) : src[i];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + static_cast<int64_t>(u) * kArThreads;
+      if (i < hi) dst[i] = v[u];
+    }
+  }
+}
+
 // Sub-range [lo, hi) (in 8-element vectors) of block b within a span of `nvec` vectors.
 __device__ __forceinline__ void block_span(int64_t nvec, int64_t& lo, int64_t& hi) {
   const int64_t per = (nvec + kArBlocks - 1) / kArBlocks;
@@ -151,22 +202,14 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_kernel(ArParams p) {
   int4* out = reinterpret_cast<int4*>(p.out);
   int4* my_slot = reinterpret_cast<int4*>(self + slot_off);
 
+  // vectors per thread in flight: U x world 16-byte loads (64 registers)
+  constexpr int U = (W == 2) ? 8 : (W == 4) ? 4 : 2;
   if (!kTwoShot) {
     int64_t lo, hi;
     block_span(nvec, lo, hi);
-    for (int64_t i = lo + threadIdx.x; i < hi; i += kArThreads) my_slot[i] = in[i];
+    copy_span(my_slot, in, lo, hi, false);
     block_barrier(p, bar0 + 1u);
-    for (int64_t i = lo + threadIdx.x; i < hi; i += kArThreads) {
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      int4 v[kArMaxRanks];
-#pragma unroll
-      for (int r = 0; r < kArMaxRanks; ++r)
-        if (r < world) v[r] = __ldcv(reinterpret_cast<const int4*>(p.peers.base[r] + slot_off) + i);
-#pragma unroll
-      for (int r = 0; r < kArMaxRanks; ++r)
-        if (r < world) accum8<T>(acc, v[r]);
-      out[i] = pack8<T>(acc);
-    }
+    reduce_span<T, W, U>(p, world, slot_off, lo, hi, out, nullptr);
   } else {
     // partition q of the message = vectors [q*pv, min((q+1)*pv, nvec))
     const int64_t pv = (nvec + world - 1) / world;
@@ -175,7 +218,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_kernel(ArParams p) {
       const int64_t len = base >= nvec ? 0 : (nvec - base < pv ? nvec - base : pv);
       int64_t lo, hi;
       block_span(len, lo, hi);
-      for (int64_t i = base + lo + threadIdx.x; i < base + hi; i += kArThreads) my_slot[i] = in[i];
+      copy_span(my_slot, in, base + lo, base + hi, false);
     }
     block_barrier(p, bar0 + 1u);
     {
@@ -183,20 +226,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_kernel(ArParams p) {
       const int64_t len = base >= nvec ? 0 : (nvec - base < pv ? nvec - base : pv);
       int64_t lo, hi;
       block_span(len, lo, hi);
-      int4* my_res = reinterpret_cast<int4*>(self + res_off);
-      for (int64_t i = base + lo + threadIdx.x; i < base + hi; i += kArThreads) {
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        int4 v[kArMaxRanks];
-#pragma unroll
-        for (int r = 0; r < kArMaxRanks; ++r)
-          if (r < world) v[r] = __ldcv(reinterpret_cast<const int4*>(p.peers.base[r] + slot_off) + i);
-#pragma unroll
-        for (int r = 0; r < kArMaxRanks; ++r)
-          if (r < world) accum8<T>(acc, v[r]);
-        const int4 o = pack8<T>(acc);
-        my_res[i] = o;
-        out[i] = o;
-      }
+      reduce_span<T, W, U>(p, world, slot_off, base + lo, base + hi, out, reinterpret_cast<int4*>(self + res_off));
     }
     block_barrier(p, bar0 + 2u);
     for (int q = 0; q < world; ++q) {
@@ -205,8 +235,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_kernel(ArParams p) {
       const int64_t len = base >= nvec ? 0 : (nvec - base < pv ? nvec - base : pv);
       int64_t lo, hi;
       block_span(len, lo, hi);
-      const int4* res = reinterpret_cast<const int4*>(p.peers.base[q] + res_off);
-      for (int64_t i = base + lo + threadIdx.x; i < base + hi; i += kArThreads) out[i] = __ldcv(res + i);
+      copy_span(out, reinterpret_cast<const int4*>(p.peers.base[q] + res_off), base + lo, base + hi, true);
     }
   }
 #if __CUDA_ARCH__ >= 900

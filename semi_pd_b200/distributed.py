@@ -8,7 +8,7 @@ vocab-sharded `lm_head` is followed by an all-gather of [bs, 2] (max, argmax) pa
 CUDA-graph capture, of the [bs, vocab/tp] logits themselves as logits_processor.py:426-427 does.
 
 Dispatch (parallel_state.py:376-436 / custom_all_reduce.py:447-480): messages up to
-`SPD_AR_MAX_BYTES` (8 MiB) → `spd_allreduce` (one-shot / two-shot over IPC-mapped peer buffers,
+`SPD_AR_MAX_BYTES` (32 MiB) → `spd_allreduce` (one-shot / two-shot over IPC-mapped peer buffers,
 graph-capturable); larger ones → the same kernel over slot-sized pieces (or, with SPD_TP_NCCL=1,
 ncclAllReduce on the worker's own process group).
 
@@ -36,7 +36,7 @@ _CPU_GROUP: Optional[dist.ProcessGroup] = None
 _DEFAULT_COMM: Optional["TpComm"] = None
 _tls = threading.local()
 
-SPD_AR_MAX_BYTES = int(os.environ.get("SPD_AR_MAX_BYTES", 8 << 20))
+SPD_AR_MAX_BYTES = int(os.environ.get("SPD_AR_MAX_BYTES", 32 << 20))
 _DT = {torch.bfloat16: 0, torch.float16: 1}
 # SPD_TP_NCCL=1: messages above SPD_AR_MAX_BYTES and the full-logits all-gather go through
 # torch.distributed's NCCL group instead of slot-sized pieces of the peer-memory kernels (A/B only)
