@@ -78,6 +78,10 @@ struct PrefillParams {
   int batch;
   int total_items;
   int use_tma;  // 0: always gather (SPD_ATTN_TMA=0)
+  // n / d for the three launch-constant divisors of the item decode (per_x = heads_x * batch,
+  // heads_x, GQA group) as multiply-high + shift: four dependent integer divisions sat on every
+  // item boundary of every role
+  uint32_t per_x_m, per_x_s, heads_x_m, heads_x_s, group_m, group_s;
   long long* trace;  // debug timeline of CTA 0 (scripts/debug_attn_prefill_timeline.py); kTrace builds only
   int trace_cap;
 };
@@ -101,6 +105,17 @@ struct PfItem {
   int kv_len;
 };
 
+// floor(n / d), n < 2^31, with (m, s) from fastdiv_magic(d)
+__device__ __forceinline__ int fastdiv(int n, uint32_t m, uint32_t s) {
+  return static_cast<int>((static_cast<uint64_t>(__umulhi(static_cast<uint32_t>(n), m)) + static_cast<uint32_t>(n)) >> s);
+}
+// Granlund-Montgomery round-up magic: s = ceil(log2 d), m = floor(2^32 * (2^s - d) / d) + 1
+inline void fastdiv_magic(uint32_t d, uint32_t& m, uint32_t& s) {
+  s = 0;
+  while ((1ull << s) < d) ++s;
+  m = static_cast<uint32_t>(((1ull << 32) * ((1ull << s) - d)) / d + 1);
+}
+
 // the three per-request values an item needs from global memory; loaded ONE ITEM AHEAD by every
 // role (the dependent loads used to sit between two items: ~1000 clk per item boundary)
 struct PfRaw {
@@ -110,7 +125,7 @@ __device__ __forceinline__ PfRaw pf_raw(const PrefillParams& p, int idx) {
   PfRaw r{0, 0, 0};
   if (idx < p.total_items) {
     const int per_x = p.heads_x * p.batch;
-    const int req = (idx - (idx / per_x) * per_x) / p.heads_x;
+    const int req = fastdiv(idx - fastdiv(idx, p.per_x_m, p.per_x_s) * per_x, p.heads_x_m, p.heads_x_s);
     r.ext = __ldg(p.extend_lens + req);
     r.pre = __ldg(p.prefix_lens + req);
     r.start = __ldg(p.extend_start_loc + req);
@@ -121,9 +136,10 @@ __device__ __forceinline__ PfRaw pf_raw(const PrefillParams& p, int idx) {
 __device__ __forceinline__ PfItem pf_item(const PrefillParams& p, int idx, const PfRaw& raw) {
   PfItem it;
   const int per_x = p.heads_x * p.batch;
-  const int qx = p.tiles_x - 1 - idx / per_x;  // heaviest (latest) query tiles first
-  const int r = idx - (idx / per_x) * per_x;
-  it.req = r / p.heads_x;
+  const int ix = fastdiv(idx, p.per_x_m, p.per_x_s);
+  const int qx = p.tiles_x - 1 - ix;  // heaviest (latest) query tiles first
+  const int r = idx - ix * per_x;
+  it.req = fastdiv(r, p.heads_x_m, p.heads_x_s);
   const int hx = r - it.req * p.heads_x;
   if (p.pair_heads) {
     it.head[0] = 2 * hx;
@@ -134,7 +150,7 @@ __device__ __forceinline__ PfItem pf_item(const PrefillParams& p, int idx, const
     it.m0[0] = 2 * qx * kPfM;
     it.m0[1] = (2 * qx + 1) * kPfM;
   }
-  it.hk = it.head[0] / (p.Hq / p.Hk);
+  it.hk = fastdiv(it.head[0], p.group_m, p.group_s);
   const int ext = raw.ext;
   it.pre = raw.pre;
   const int start = raw.start;
@@ -555,6 +571,74 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint32_t u = 0;  // units processed by this warpgroup (all items); unit of the tile = u % kNU
     uint32_t tn = 0;
     const bool tracer = kTrace && (threadIdx.x & 127) == 0;
+    // ---- epilogue: O / l, TMEM -> registers -> global ----
+    // (Tried in round 2: DEFERRING it until the next item's first unit has been exponentiated, so
+    // that the ~1500-1900 clk drain of the item's last PV is spent on useful work.  The drain wait
+    // did shrink to ~700 clk, but o_free — and with it the next item's first PV — moved later by
+    // a whole softmax pass, and the kernel got 5 % slower at 8 x 1024; not kept.)
+    float e_l = 0.f;  // state of the item being written out
+    int e_rows = 0, e_head = 0, e_q_row0 = 0;
+    uint32_t e_u = 0;
+    auto epilogue = [&]() {
+      // last unit = half b of the last tile; S of that unit complete => PV(b) of the tile before is
+      // complete, so only this one phase of pv_done[w][b] can be outstanding; PV(b) complete => PV(a)
+      mbar_wait(&pv_done[w * 2 + (kNU - 1)], ((e_u - 1) / kNU) & 1);
+      tc_fence_after_sync();
+      if (tracer) pf_trace<kTrace>(p, w, tn, 0x500);  // last PV complete
+      const float inv_l = e_l > 0.f ? 1.f / e_l : 0.f;
+      // A full tile leaves through shared memory and one TMA store per 64-column block: with one
+      // thread per row, direct 16-byte stores touch 32 different lines per warp instruction and
+      // the 128 rows x 256 B took ~5900 clk per item (in-kernel timeline, round 2) — a quarter of
+      // the kernel at 1024-token prompts.  A ragged last tile (fewer than 128 rows) must not write
+      // the rows of the next request and keeps the direct path.
+      const bool full_tile = e_rows == kPfM;
+      uint8_t* stage = sO + w * (kPfStage / 2);
+      T* dst = reinterpret_cast<T*>(p.out) + static_cast<int64_t>(e_q_row0 + row) * p.out_stride +
+               static_cast<int64_t>(e_head) * kPfD;
+#pragma unroll 1
+      for (int c = 0; c < kPfD; c += 64) {
+        uint32_t a[32], b[32];
+        tmem_ld_32x32b_x32(to + c, a);
+        tmem_ld_32x32b_x32(to + c + 32, b);
+        tmem_ld_wait();
+        if (c == 64) {
+          // every O column of this warp is in registers: the next item's first PV may overwrite it
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_free[w]);
+        }
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[i].x = pack2<T>(__uint_as_float(a[8 * i]) * inv_l, __uint_as_float(a[8 * i + 1]) * inv_l);
+          v[i].y = pack2<T>(__uint_as_float(a[8 * i + 2]) * inv_l, __uint_as_float(a[8 * i + 3]) * inv_l);
+          v[i].z = pack2<T>(__uint_as_float(a[8 * i + 4]) * inv_l, __uint_as_float(a[8 * i + 5]) * inv_l);
+          v[i].w = pack2<T>(__uint_as_float(a[8 * i + 6]) * inv_l, __uint_as_float(a[8 * i + 7]) * inv_l);
+          v[4 + i].x = pack2<T>(__uint_as_float(b[8 * i]) * inv_l, __uint_as_float(b[8 * i + 1]) * inv_l);
+          v[4 + i].y = pack2<T>(__uint_as_float(b[8 * i + 2]) * inv_l, __uint_as_float(b[8 * i + 3]) * inv_l);
+          v[4 + i].z = pack2<T>(__uint_as_float(b[8 * i + 4]) * inv_l, __uint_as_float(b[8 * i + 5]) * inv_l);
+          v[4 + i].w = pack2<T>(__uint_as_float(b[8 * i + 6]) * inv_l, __uint_as_float(b[8 * i + 7]) * inv_l);
+        }
+        if (full_tile) {
+          // the block's previous TMA store has finished READING the staging memory
+          if (row == 0) bulk_wait_group_read0();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + w) : "memory");
+#pragma unroll
+          for (int i = 0; i < 8; ++i)  // [128 rows x 128 B], 128-byte swizzle: chunk ^ (row % 8)
+            *reinterpret_cast<uint4*>(stage + row * 128 + ((i ^ (row & 7)) << 4)) = v[i];
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + w) : "memory");
+          if (row == 0) {
+            tma_store_2d(&tmO, stage, e_head * kPfD + c, e_q_row0);
+            bulk_commit_group();
+          }
+        } else if (row < e_rows) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(dst + c + 8 * i) = v[i];
+        }
+      }
+      if (tracer) pf_trace<kTrace>(p, w, tn, 0x600);  // O stored
+    };
     int idx = pf_rank(0, cta, ncta);
     PfRaw raw = pf_raw(p, idx);
     for (int k = 0; idx < p.total_items; ++k) {
@@ -629,66 +713,13 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (lane == 0) mbar_arrive(&p_full[w * 2 + h]);
         if (tracer) pf_trace<kTrace>(p, w, tn, 0x300 + h);  // P published
       }
-      if (tracer) pf_trace<kTrace>(p, w, tn, 0x400);  // epilogue begins
-      // ---- epilogue: O / l, TMEM -> registers -> global ----
-      // last unit = half b of the last tile; S of that unit complete => PV(b) of the tile before is
-      // complete, so only this one phase of pv_done[w][b] can be outstanding; PV(b) complete => PV(a)
-      mbar_wait(&pv_done[w * 2 + (kNU - 1)], ((u - 1) / kNU) & 1);
-      tc_fence_after_sync();
-      if (tracer) pf_trace<kTrace>(p, w, tn, 0x500);  // last PV complete
-      const float inv_l = l > 0.f ? 1.f / l : 0.f;
-      // A full tile leaves through shared memory and one TMA store per 64-column block: with one
-      // thread per row, direct 16-byte stores touch 32 different lines per warp instruction and
-      // the 128 rows x 256 B took ~5900 clk per item (in-kernel timeline, round 2) — a quarter of
-      // the kernel at 1024-token prompts.  A ragged last tile (rows_valid < 128) must not write
-      // the rows of the next request and keeps the direct path.
-      const bool full_tile = rows_valid == kPfM;
-      uint8_t* stage = sO + w * (kPfStage / 2);
-      T* dst = reinterpret_cast<T*>(p.out) + static_cast<int64_t>(q_row0 + row) * p.out_stride +
-               static_cast<int64_t>(head) * kPfD;
-#pragma unroll 1
-      for (int c = 0; c < kPfD; c += 64) {
-        uint32_t a[32], b[32];
-        tmem_ld_32x32b_x32(to + c, a);
-        tmem_ld_32x32b_x32(to + c + 32, b);
-        tmem_ld_wait();
-        if (c == 64) {
-          // every O column of this warp is in registers: the next item's first PV may overwrite it
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&o_free[w]);
-        }
-        uint4 v[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          v[i].x = pack2<T>(__uint_as_float(a[8 * i]) * inv_l, __uint_as_float(a[8 * i + 1]) * inv_l);
-          v[i].y = pack2<T>(__uint_as_float(a[8 * i + 2]) * inv_l, __uint_as_float(a[8 * i + 3]) * inv_l);
-          v[i].z = pack2<T>(__uint_as_float(a[8 * i + 4]) * inv_l, __uint_as_float(a[8 * i + 5]) * inv_l);
-          v[i].w = pack2<T>(__uint_as_float(a[8 * i + 6]) * inv_l, __uint_as_float(a[8 * i + 7]) * inv_l);
-          v[4 + i].x = pack2<T>(__uint_as_float(b[8 * i]) * inv_l, __uint_as_float(b[8 * i + 1]) * inv_l);
-          v[4 + i].y = pack2<T>(__uint_as_float(b[8 * i + 2]) * inv_l, __uint_as_float(b[8 * i + 3]) * inv_l);
-          v[4 + i].z = pack2<T>(__uint_as_float(b[8 * i + 4]) * inv_l, __uint_as_float(b[8 * i + 5]) * inv_l);
-          v[4 + i].w = pack2<T>(__uint_as_float(b[8 * i + 6]) * inv_l, __uint_as_float(b[8 * i + 7]) * inv_l);
-        }
-        if (full_tile) {
-          // the block's previous TMA store has finished READING the staging memory
-          if (row == 0) bulk_wait_group_read0();
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + w) : "memory");
-#pragma unroll
-          for (int i = 0; i < 8; ++i)  // [128 rows x 128 B], 128-byte swizzle: chunk ^ (row % 8)
-            *reinterpret_cast<uint4*>(stage + row * 128 + ((i ^ (row & 7)) << 4)) = v[i];
-          fence_proxy_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + w) : "memory");
-          if (row == 0) {
-            tma_store_2d(&tmO, stage, head * kPfD + c, q_row0);
-            bulk_commit_group();
-          }
-        } else if (row < rows_valid) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(dst + c + 8 * i) = v[i];
-        }
-      }
-      if (tracer) pf_trace<kTrace>(p, w, tn, 0x600);  // O stored
+      if (tracer) pf_trace<kTrace>(p, w, tn, 0x400);  // item done
+      e_l = l;
+      e_rows = rows_valid;
+      e_head = head;
+      e_q_row0 = q_row0;
+      e_u = u;
+      epilogue();
     }
   }
 
@@ -757,6 +788,9 @@ extern "C" int spd_attn_prefill_ragged(void* out, const void* q, const void* k_p
   const int64_t total = static_cast<int64_t>(p.tiles_x) * p.heads_x * batch;
   SPD_REQUIRE(total < (1ll << 30), SPD_E_SHAPE, "spd_attn_prefill_ragged: too many work items");
   p.total_items = static_cast<int>(total);
+  fastdiv_magic(static_cast<uint32_t>(p.heads_x) * static_cast<uint32_t>(p.batch), p.per_x_m, p.per_x_s);
+  fastdiv_magic(static_cast<uint32_t>(p.heads_x), p.heads_x_m, p.heads_x_s);
+  fastdiv_magic(static_cast<uint32_t>(num_q_heads / num_kv_heads), p.group_m, p.group_s);
   CUtensorMap tq, tk, tv, to;
   if ((rc = get_tmap(&tq, q, static_cast<uint64_t>(total_tokens),
                      static_cast<uint64_t>(num_q_heads) * head_dim, static_cast<uint64_t>(q_stride), kPfM)))
