@@ -227,8 +227,9 @@ int spd_attn_decode_simt(void* out, const void* q, const void* k_pool, const voi
  * of SURVEY §8b's export list.  Replaces the custom all-reduce the reference sends every
  * RowParallelLinear output below 8 MiB through (S/layers/linear.py:1265-1266 →
  * S/distributed/parallel_state.py:376-436 → device_communicators/custom_all_reduce.py:147-160,
- * 447-480; alternative K/csrc/allreduce/trt_reduce_internal.cu:190-300); larger messages (prefill
- * batches) go to ncclAllReduce as in parallel_state.py:431-436.
+ * 447-480; alternative K/csrc/allreduce/trt_reduce_internal.cu:190-300); the reference sends larger
+ * messages (prefill batches) to ncclAllReduce (parallel_state.py:431-436) — the host side here
+ * passes them through this entry point in pieces of at most max_message_bytes.
  *
  * spd_comm_create allocates this rank's symmetric buffer (3 x max_message_bytes + 8 KB) on the
  * current device and writes its 64-byte cudaIpcMemHandle to ipc_handle_out; the caller gathers
