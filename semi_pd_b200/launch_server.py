@@ -27,24 +27,31 @@ def prepare_server_args(argv: List[str]) -> ServerArgs:
     return sa
 
 
-def launch_server(server_args: ServerArgs):
+def build_app(server_args: ServerArgs, model_config=None, gpu_id: int = 0):
+    """The FastAPI app + the engine behind it (separate from `launch_server` so that a test can
+    drive the endpoints in-process).  A request the engine rejects (input longer than the context
+    / KV pool allows) is answered with 400, as the reference aborts it with BAD_REQUEST
+    (managers/utils.py:10-44)."""
     if not server_args.enable_semi_pd:
         raise SystemExit("this build implements the semi-PD path: pass --enable-semi-pd")
     if server_args.tp_size != 1:
-        raise SystemExit("launch_server runs TP=1 replicas; use bench.py --gpus N for N replicas")
-    import uvicorn
-    from fastapi import FastAPI
+        raise SystemExit("launch_server runs TP=1 replicas; use bench.py --gpus N for the TP engine")
+    from fastapi import FastAPI, HTTPException
     from pydantic import BaseModel
 
     from .semi_pd_scheduler import SemiPDEngine
 
-    engine = SemiPDEngine(server_args, gpu_id=0, partition=getattr(server_args, "sm_partition", "green"))
+    engine = SemiPDEngine(server_args, gpu_id=gpu_id, model_config=model_config,
+                          partition=getattr(server_args, "sm_partition", "green"))
     engine.warmup()
     results, cond = {}, threading.Condition()
 
     def collector():
-        while True:
-            req = engine.decode.finished.get()
+        while not engine._closed:
+            try:
+                req = engine.decode.finished.get(timeout=0.2)
+            except Exception:  # noqa: BLE001  (queue.Empty)
+                continue
             with cond:
                 results[req.rid] = req
                 cond.notify_all()
@@ -70,16 +77,26 @@ def launch_server(server_args: ServerArgs):
     def generate(r: GenerateReq):
         sp = r.sampling_params or {}
         t0 = time.perf_counter()
-        rid = engine.submit(r.input_ids, int(sp.get("max_new_tokens", 128)),
-                            ignore_eos=bool(sp.get("ignore_eos", True)))
+        try:
+            rid = engine.submit(r.input_ids, int(sp.get("max_new_tokens", 128)),
+                                ignore_eos=bool(sp.get("ignore_eos", True)))
+        except ValueError as e:
+            raise HTTPException(status_code=400, detail=str(e))
         with cond:
-            cond.wait_for(lambda: rid in results, timeout=600)
+            if not cond.wait_for(lambda: rid in results, timeout=600):
+                raise HTTPException(status_code=504, detail="generation timed out")
             req = results.pop(rid)
         return {"output_ids": req.output_ids,
                 "meta_info": {"id": rid, "prompt_tokens": len(r.input_ids),
                               "completion_tokens": len(req.output_ids),
                               "ttft": req.first_token_time - t0, "e2e_latency": time.perf_counter() - t0}}
 
+    return app, engine
+
+
+def launch_server(server_args: ServerArgs):
+    import uvicorn
+    app, _ = build_app(server_args)
     uvicorn.run(app, host=server_args.host, port=server_args.port, log_level="warning")
 
 

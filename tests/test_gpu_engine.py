@@ -241,3 +241,66 @@ def test_request_validation_and_two_engines_in_one_process():
         else:
             assert part is first_part                       # green contexts are pooled, not leaked
             assert torch.cuda.memory_allocated() <= mem_after_first + (8 << 20)
+
+
+def test_http_generate_endpoint_in_process():
+    """`python -m sglang.launch_server --enable-semi-pd` serves /generate in token-id space: the
+    same FastAPI app driven in-process (starlette TestClient), concurrent requests from a thread
+    pool, ids equal to the engine-free sequential oracle; an over-long input is a 400."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from starlette.testclient import TestClient
+
+    import semi_pd_b200.model_runner as MR
+    from semi_pd_b200.configs import ModelConfig
+    from semi_pd_b200.launch_server import build_app, prepare_server_args
+
+    dtype = torch.float16
+    ocfg = O.OracleLlamaConfig(**CFG)
+    weights = O.make_weights(ocfg, dtype, seed=21)
+    sa = prepare_server_args(["--model-path", "tiny", "--enable-semi-pd", "--dtype", "float16",
+                              "--load-format", "external", "--max-total-tokens", "8192",
+                              "--max-running-requests", "16", "--context-length", "512"])
+    orig = MR.ModelRunner.load_model
+
+    def load_with_weights(self):
+        orig(self)
+        self.model.load_weights(weights.items())
+
+    MR.ModelRunner.load_model = load_with_weights
+    try:
+        app, engine = build_app(sa, model_config=ModelConfig(name="tiny", **CFG))
+    finally:
+        MR.ModelRunner.load_model = orig
+    try:
+        client = TestClient(app)
+        assert client.get("/health").json() == {"status": "ok"}
+        info = client.get("/get_server_info").json()
+        assert info["prefill_sms"] + info["decode_sms"] <= 148 and info["max_total_num_tokens"] >= 8192
+        lens, n_new = [7, 130, 33, 64], 6
+        prompts = [[(5 + 3 * i + 11 * j) % CFG["vocab_size"] for i in range(n)] for j, n in enumerate(lens)]
+
+        def post(p):
+            return client.post("/generate", json={"input_ids": p, "sampling_params": {"max_new_tokens": n_new}})
+
+        with ThreadPoolExecutor(4) as ex:
+            outs = list(ex.map(post, prompts))
+        for p, r in zip(prompts, outs):
+            assert r.status_code == 200
+            body = r.json()
+            assert body["meta_info"]["prompt_tokens"] == len(p) and body["meta_info"]["completion_tokens"] == n_new
+            m = O.LlamaOracle(ocfg, weights, kv_slots=1024, max_reqs=2, max_ctx=520, compute="fp32")
+            s = O.OracleSession(m, 1024, 2)
+            rids, logits, _ = s.extend([p])
+            for k in range(n_new):
+                top2 = logits.topk(2, -1).values[0]
+                if float(top2[0] - top2[1]) <= 2e-2:
+                    break
+                t = int(logits.argmax(-1)[0])
+                assert body["output_ids"][k] == t
+                if k + 1 < n_new:
+                    logits, _ = s.decode(rids, [t])
+        bad = client.post("/generate", json={"input_ids": list(range(600)), "sampling_params": {"max_new_tokens": 4}})
+        assert bad.status_code == 400 and "exceeds" in bad.json()["detail"]
+    finally:
+        engine.shutdown()
