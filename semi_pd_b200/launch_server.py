@@ -12,7 +12,15 @@ import threading
 import time
 from typing import List, Optional
 
+from pydantic import BaseModel
+
 from .configs import ServerArgs
+
+
+class GenerateReq(BaseModel):
+    """Body of POST /generate (io_struct.GenerateReqInput restricted to token ids)."""
+    input_ids: List[int]
+    sampling_params: Optional[dict] = None
 
 
 def prepare_server_args(argv: List[str]) -> ServerArgs:
@@ -37,7 +45,6 @@ def build_app(server_args: ServerArgs, model_config=None, gpu_id: int = 0):
     if server_args.tp_size != 1:
         raise SystemExit("launch_server runs TP=1 replicas; use bench.py --gpus N for the TP engine")
     from fastapi import FastAPI, HTTPException
-    from pydantic import BaseModel
 
     from .semi_pd_scheduler import SemiPDEngine
 
@@ -58,10 +65,6 @@ def build_app(server_args: ServerArgs, model_config=None, gpu_id: int = 0):
 
     threading.Thread(target=collector, daemon=True).start()
     app = FastAPI()
-
-    class GenerateReq(BaseModel):
-        input_ids: List[int]
-        sampling_params: Optional[dict] = None
 
     @app.get("/health")
     def health():
