@@ -558,8 +558,22 @@ class SemiPDDecodeScheduler(SemiPDScheduler):
             if req.finished():
                 self._release(req)
 
-    def _drain_results(self, all_of_them: bool = False, keep: int = 1):
+    def _drain_results(self, all_of_them: bool = False, keep: int = 1, service_inbox: bool = False):
+        """Read back the sampled ids of the oldest launched steps.  With `service_inbox` the wait
+        for a step that is still running is spent on the inbox: a new request is admitted (so the
+        prefill worker starts on it) and a prefill report is taken (so its first token is
+        delivered) NOW instead of after the step — at a 4-5 ms decode step each of the two used
+        to add half a step to every TTFT.  TP = 1 only: under TP the inbox is processed in
+        lockstep, once per iteration."""
         while self.result_queue and (all_of_them or len(self.result_queue) > keep):
+            if service_inbox and self.tp_size == 1:
+                ev = self.result_queue[0][3]
+                while not ev.query():
+                    if self.inbox.empty():
+                        time.sleep(0.00005)
+                    else:
+                        self.recv_requests()
+                        self.maybe_schedule_prefill()
             self.process_batch_result_decode(*self.result_queue.popleft())
 
     def event_loop(self):
@@ -575,7 +589,7 @@ class SemiPDDecodeScheduler(SemiPDScheduler):
             batch = self.get_next_batch_to_run()
             if batch is not None:
                 self.run_batch(batch)
-                self._drain_results(keep=1)
+                self._drain_results(keep=1, service_inbox=True)
                 idle_spins = 0
             else:
                 self._drain_results(all_of_them=True)
