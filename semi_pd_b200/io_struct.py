@@ -47,6 +47,9 @@ class BatchProcessPrefillResultReq:
     next_token_logits: Optional[Any] = None
     # recorded on the prefill stream after the forward (KV rows of the batch are in the pool)
     done_event: Any = None
+    # host timestamps of the prefill worker (batch fetched, forward launched, ids read back):
+    # TTFT breakdown of scripts/debug_ttft_breakdown.py
+    timing: Optional[tuple] = None
 
 
 @dataclasses.dataclass

@@ -222,6 +222,7 @@ class SemiPDPrefillScheduler(SemiPDScheduler):
             ids.copy_(next_token_ids[:n], non_blocking=True)
         done = torch.cuda.Event()
         done.record(self.stream)
+        batch.t_fetched, batch.t_launched = t0, time.perf_counter()
         return batch, ids, t0, done
 
     def process_batch_result_prefill(self, batch: ScheduleBatch, ids, t0: float, done):
@@ -232,7 +233,8 @@ class SemiPDPrefillScheduler(SemiPDScheduler):
         if not self.device_resident:
             ids = ids.tolist()
         self.prefill_busy_s += time.perf_counter() - t0
-        msg = BatchProcessPrefillResultReq(next_token_ids=ids, done_event=done)
+        msg = BatchProcessPrefillResultReq(next_token_ids=ids, done_event=done,
+                                           timing=(batch.t_fetched, batch.t_launched, time.perf_counter()))
         if self.tp_size > 1 and self.tp_rank != 0:
             self.local_result_queue.put(msg)
         else:
@@ -404,6 +406,7 @@ class SemiPDDecodeScheduler(SemiPDScheduler):
         new_batch.prepare_for_extend()
         # the request (if any) whose prefill is NOT complete after this batch
         new_batch.chunked_req = self.chunked_req
+        new_batch.t_admitted = time.perf_counter()
         self.scheduled_prefill_batches.append(new_batch)
         return new_batch
 
@@ -437,6 +440,7 @@ class SemiPDDecodeScheduler(SemiPDScheduler):
             req.launched_tokens = 1
             if req.first_token_time is None:  # a retracted request keeps its original TTFT
                 req.first_token_time = now
+                req.ttft_stamps = (getattr(batch, "t_admitted", None),) + tuple(recv_req.timing or ())
             req.token_times.append(now)
             req.check_finished()
             if self.token_callback:
