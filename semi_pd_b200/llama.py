@@ -8,6 +8,7 @@ order.  Differences, all fusions that remove HBM round trips
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Iterable, Optional, Tuple
 
 import torch
@@ -19,7 +20,8 @@ from .layers import (LogitsProcessor, MergedColumnParallelLinear, ParallelLMHead
                      RMSNorm, RowParallelLinear, SiluAndMul, VocabParallelEmbedding, get_rope)
 
 # tokens above which the gate_up GEMM runs in the (non-swapped) prefill regime and can fuse SiLU·mul
-_FUSED_SILU_MIN_TOKENS = 257
+# SPD_FUSED_SILU_MIN_TOKENS: A/B knob (a huge value routes prefill through the plain GEMM + SiLU·mul kernel)
+_FUSED_SILU_MIN_TOKENS = int(os.environ.get("SPD_FUSED_SILU_MIN_TOKENS", 257))
 
 
 class LlamaMLP:
