@@ -35,7 +35,7 @@ def clocks(stop, out):
         time.sleep(0.05)
 
 
-def run(name, fns, flops, reps=40):
+def run(name, fns, flops, reps=int(__import__('os').environ.get('REPS', 400))):
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         for f in fns:

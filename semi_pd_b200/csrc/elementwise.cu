@@ -157,7 +157,7 @@ silu_and_mul_kernel(T* __restrict__ out, const T* __restrict__ x, int64_t tokens
     vec8_to_f32<T>(row[c], g);
     vec8_to_f32<T>(row[nvec_row + c], u);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = g[j] / (1.0f + __expf(-g[j])) * u[j];
+    for (int j = 0; j < 8; ++j) o[j] = silu_f32(g[j]) * u[j];
     reinterpret_cast<Vec8*>(out + t * d)[c] = f32_to_vec8<T>(o);
   }
 }

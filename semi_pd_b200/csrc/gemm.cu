@@ -439,7 +439,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             // gate_up_proj output is rounded to T before SiluAndMul reads it
             const float g = to_f32<T>(from_f32<T>(__uint_as_float(r[j])));
             const float up = to_f32<T>(from_f32<T>(__uint_as_float(u[j])));
-            v[j] = g / (1.0f + __expf(-g)) * up;
+            v[j] = silu_f32(g) * up;
           }
         } else {
           tmem_ld_wait();

@@ -230,7 +230,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // gate_up_proj output is rounded to T before SiluAndMul reads it
             const float g = to_f32<T>(from_f32<T>(__uint_as_float(r[j])));
             const float up = to_f32<T>(from_f32<T>(__uint_as_float(u[j])));
-            v[j] = g / (1.0f + __expf(-g)) * up;
+            v[j] = silu_f32(g) * up;
           }
         } else {
           tmem_ld_wait();

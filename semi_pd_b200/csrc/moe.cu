@@ -216,8 +216,8 @@ moe_dense_act_kernel(T* __restrict__ act, const T* __restrict__ gate_up, const i
       for (int q = 0; q < 4; ++q) {
         const float2 gf = unpack2<T>(g.w[q]), uf = unpack2<T>(u.w[q]);
         // silu(gate) * up rounded to T (what the expert's down projection reads), then the weight
-        const float a = to_f32<T>(from_f32<T>(gf.x / (1.0f + __expf(-gf.x)) * uf.x));
-        const float b = to_f32<T>(from_f32<T>(gf.y / (1.0f + __expf(-gf.y)) * uf.y));
+        const float a = to_f32<T>(from_f32<T>(silu_f32(gf.x) * uf.x));
+        const float b = to_f32<T>(from_f32<T>(silu_f32(gf.y) * uf.y));
         o.w[q] = pack2<T>(w * a, w * b);
       }
     }

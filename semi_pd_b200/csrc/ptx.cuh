@@ -366,6 +366,15 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// SiLU(g) = g / (1 + exp(-g)) with the fast division.  The reference's kernel is the same
+// expression compiled with -use_fast_math (sgl-kernel/csrc/elementwise/activation.cu:23,
+// sgl-kernel/setup.py:182,194), i.e. this instruction sequence.  The IEEE division it replaces
+// here (FCHK + a slow-path call per element) made the fused W_gate_up epilogue the bottleneck of
+// the prefill GEMM under sustained load: 1062 -> 1376 TF/s back to back at M = 8192
+// (profiles/r02_gateup_sustained.log).  Denominator >= 1, and it is finite wherever the quotient
+// is not already below bf16's range, so __fdividef's 2^126 caveat never applies.
+__device__ __forceinline__ float silu_f32(float g) { return __fdividef(g, 1.0f + __expf(-g)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
