@@ -335,3 +335,61 @@ def test_deepseek_decode_dense_moe_path_and_cuda_graph():
         lc = os_.decode(rids, tok)
         assert (lg - lc).abs().max().item() < tol
         tok = lc.argmax(-1).tolist()
+
+
+def test_deepseek_semi_pd_engine_matches_sequential_oracle():
+    """BASELINE configs[3] end to end: the semi-PD engine (prefill and decode workers on disjoint SM
+    partitions, chunked prefill, decode CUDA graphs over the latent pool) serving the mini
+    DeepSeek-V2 model produces the sequential oracle's greedy tokens.  A step is compared only
+    where the oracle's top-1 / top-2 margin exceeds 2e-2 and no router decision of that forward
+    is a near-tie (see test_deepseek_mini_model_matches_oracle)."""
+    import semi_pd_b200.model_runner as MR
+    from semi_pd_b200.configs import ModelConfig, ServerArgs
+    from semi_pd_b200.semi_pd_scheduler import SemiPDEngine
+
+    dtype = torch.float16
+    ocfg = D.DeepseekOracleConfig(**MINI, rope_scaling=None)
+    weights = _weights(ocfg, dtype)
+    mcfg = ModelConfig(name="mini-deepseek", model_type="deepseek_v2", num_key_value_heads=MINI["num_attention_heads"],
+                       head_dim=192, rms_norm_eps=ocfg.rms_norm_eps, rope_theta=ocfg.rope_theta, rope_scaling=None,
+                       **MINI)
+    sa = ServerArgs(model_path="mini-deepseek", dtype="float16", load_format="external", max_total_tokens=8192,
+                    max_running_requests=16, context_length=1024, enable_semi_pd=True, cuda_graph_bs=[1, 2, 4, 8, 16],
+                    chunked_prefill_size=96, max_prefill_tokens=4096)
+    orig = MR.ModelRunner.load_model
+
+    def load_with_weights(self):
+        orig(self)
+        self.model.load_weights(weights.items())
+
+    MR.ModelRunner.load_model = load_with_weights
+    try:
+        eng = SemiPDEngine(sa, gpu_id=0, model_config=mcfg, prefill_sm_percent=50, decode_sm_percent=50)
+    finally:
+        MR.ModelRunner.load_model = orig
+    lens, n_new = [5, 130, 17, 64, 257, 33], 8
+    prompts = [[(11 + 7 * i + 29 * j) % MINI["vocab_size"] for i in range(n)] for j, n in enumerate(lens)]
+    try:
+        assert eng.d_worker.model_runner.cuda_graph_runner is not None
+        rids = [eng.submit(p, n_new) for p in prompts]
+        done = {r.rid: r for r in eng.wait(len(prompts), timeout=120)}
+        got = [done[r].output_ids for r in rids]
+    finally:
+        eng.shutdown()
+    checked = bad = 0
+    for p, g_ in zip(prompts, got):
+        assert len(g_) == n_new
+        oracle = D.DeepseekOracle(ocfg, weights, kv_slots=2048, max_reqs=4, max_ctx=1100)
+        s = D.DeepseekSession(oracle, 2048, seed=5)
+        r_o, logits = s.extend([p])
+        for k in range(n_new):
+            top2 = logits.topk(2, -1).values[0]
+            near_tie = oracle.router_margins and float(torch.stack(oracle.router_margins).min()) < 4e-3
+            if float(top2[0] - top2[1]) <= 2e-2 or near_tie:
+                break  # from here on the two sequences may legitimately differ
+            t = int(logits.argmax(-1)[0])
+            bad += int(g_[k] != t)
+            checked += 1
+            if k + 1 < n_new:
+                logits = s.decode(r_o, [t])
+    assert bad == 0 and checked >= 12, (checked, bad)
