@@ -66,3 +66,73 @@ def test_tp2_gloo_matches_unsharded():
         ret = m.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
         assert dict(ret) == {0: True, 1: True}
+
+
+def _lockstep_worker(rank, world, port, ret):
+    """Drives SemiPDDecodeScheduler.recv_requests — the per-iteration message broadcast that keeps
+    the decode schedulers of all TP ranks in lockstep (scheduler.py:599-659) — on CPU: the class
+    is instantiated without its GPU members and the two handlers are recorded instead of run."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import queue
+    import threading
+
+    import torch.distributed as dist
+
+    from semi_pd_b200.io_struct import BatchProcessPrefillResultReq, TokenizedGenerateReqInput
+    from semi_pd_b200.schedule_batch import SamplingParams
+    from semi_pd_b200.semi_pd_scheduler import SemiPDDecodeScheduler
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    s = SemiPDDecodeScheduler.__new__(SemiPDDecodeScheduler)
+    s.tp_rank, s.tp_size, s.cpu_group = rank, world, dist.group.WORLD
+    s.inbox, s.local_prefill_results, s.send_to_p_instance = queue.Queue(), queue.Queue(), queue.Queue()
+    s.stop_flag, s._stop_broadcast = threading.Event(), False
+    log = []
+    s.handle_generate_request = lambda m: log.append(("gen", m.rid, tuple(m.input_ids), m.sampling_params.max_new_tokens))
+    s.process_prefill_result = lambda m: log.append(("prefill_result", tuple(m.next_token_ids)))
+    if rank == 0:
+        # iteration 1: two requests; iteration 2: nothing; iteration 3: a prefill report and a
+        # request; iteration 4: stop (set before the iteration starts)
+        script = [[TokenizedGenerateReqInput(rid="a", input_text="", input_ids=[1, 2, 3],
+                                             sampling_params=SamplingParams(max_new_tokens=5), arrival_time=0.0),
+                   TokenizedGenerateReqInput(rid="b", input_text="", input_ids=[4],
+                                             sampling_params=SamplingParams(max_new_tokens=2), arrival_time=0.0)],
+                  [],
+                  [BatchProcessPrefillResultReq(next_token_ids=[7, 8]),
+                   TokenizedGenerateReqInput(rid="c", input_text="", input_ids=[9, 9],
+                                             sampling_params=SamplingParams(max_new_tokens=1), arrival_time=0.0)]]
+    else:
+        script = [[], [], []]
+        # this rank's own prefill worker reports the same batch (its ids are identical)
+        s.local_prefill_results.put(BatchProcessPrefillResultReq(next_token_ids=[7, 8]))
+    iters = 0
+    for msgs in script:
+        for m in msgs:
+            s.inbox.put(m)
+        s.recv_requests()
+        iters += 1
+        assert not s._stop_broadcast
+    if rank == 0:
+        s.stop_flag.set()
+    s.recv_requests()
+    iters += 1
+    ret[rank] = (log, iters, s._stop_broadcast, s.stop_flag.is_set(),
+                 [m.rid for m in list(s.send_to_p_instance.queue)])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tp2_decode_schedulers_process_identical_messages_and_stop_together():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_lockstep_worker, args=(world, port, ret), nprocs=world, join=True)
+        out = dict(ret)
+    log0, it0, stop0, _, _ = out[0]
+    log1, it1, stop1, flag1, to_p1 = out[1]
+    assert log0 == log1 == [("gen", "a", (1, 2, 3), 5), ("gen", "b", (4,), 2), ("prefill_result", (7, 8)),
+                            ("gen", "c", (9, 9), 1)]
+    assert it0 == it1 == 4 and stop0 and stop1 and flag1   # both leave in the SAME iteration
+    assert to_p1 == ["a", "b", "c"]                        # rank 1's prefill worker learns every request
