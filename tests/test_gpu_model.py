@@ -22,6 +22,10 @@ L8B2 = dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=2, num_
 # (the cross-rank sum itself is covered by tests/test_gpu_tp.py and bench.py's tp_parity)
 L70B_TP8_RANK = dict(hidden_size=8192, intermediate_size=3584, num_hidden_layers=2, num_attention_heads=8,
                      num_key_value_heads=1, head_dim=128, vocab_size=4096, max_position_embeddings=4096)
+# ... and one rank of Llama-3-8B at TP = 8 (4 query heads over 1 kv head, 1792 FFN columns, the
+# 128256 / 8 = 16032-row vocab shard whose last GEMM tile is partial)
+L8B_TP8_RANK = dict(hidden_size=4096, intermediate_size=1792, num_hidden_layers=2, num_attention_heads=4,
+                    num_key_value_heads=1, head_dim=128, vocab_size=16032, max_position_embeddings=4096)
 TOL = {torch.float16: 1e-2, torch.bfloat16: 6e-2}
 
 
@@ -38,7 +42,8 @@ def _check_ids(logits_cpu, ids_gpu, margin=2e-2):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("cfg", [TINY, L8B2, L70B_TP8_RANK], ids=["tiny", "8b-2layer", "70b-tp8-rank-2layer"])
+@pytest.mark.parametrize("cfg", [TINY, L8B2, L70B_TP8_RANK, L8B_TP8_RANK],
+                         ids=["tiny", "8b-2layer", "70b-tp8-rank-2layer", "8b-tp8-rank-2layer"])
 def test_extend_then_decode_matches_oracle(cfg, dtype):
     mr, oracle, ocfg = make_runner(cfg, dtype)
     gs, os_ = GpuSession(mr), O.OracleSession(oracle, 4096, 17)
