@@ -257,6 +257,15 @@ int64_t spd_comm_max_bytes(const spd_comm_t* comm);
 int spd_comm_status(spd_comm_t* comm, int* timed_out);
 int spd_allreduce(spd_comm_t* comm, void* out, const void* in, int64_t count, int dtype, int algo,
                   spd_stream_t stream);
+/* The all-reduce fused with its consumer (round 2): x = sum over ranks of in[rows, dim];
+ * residual += x (rounded to the dtype as fused_add_rmsnorm stores it); out = RMSNorm(residual) * weight
+ * — S/layers/linear.py:1265-1266 (tensor_model_parallel_all_reduce after o_proj / down_proj)
+ * followed by S/layers/layernorm.py:46-57 (fused_add_rmsnorm) in ONE kernel over the peer-mapped
+ * slots.  Bit-identical to spd_allreduce + spd_fused_add_rmsnorm.  dim % 8 == 0, dim <= 8192,
+ * rows * dim * 2 <= max_message_bytes; out may alias in.  Same ordering / graph-capture rules. */
+int spd_allreduce_add_rmsnorm(spd_comm_t* comm, void* out, const void* in, void* residual,
+                              const void* weight, int64_t rows, int64_t dim, float eps, int dtype,
+                              spd_stream_t stream);
 /* out[r * bytes_per_rank + i] = rank r's in[i] (bytes_per_rank % 16 == 0, <= max_message_bytes):
  * the all-gather after the vocab-sharded lm_head (S/layers/logits_processor.py:426-427), here of
  * the per-shard (max, argmax) rows below — and of small logits blocks.  Same ordering /

@@ -72,6 +72,7 @@ SIGNATURES = {
     "spd_comm_max_bytes": (_i64, [_p]),
     "spd_comm_status": (_i, [_p, C.POINTER(_i)]),
     "spd_allreduce": (_i, [_p, _p, _p, _i64, _i, _i, _p]),
+    "spd_allreduce_add_rmsnorm": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _f, _i, _p]),
     "spd_allgather": (_i, [_p, _p, _p, _i64, _p]),
     "spd_comm_destroy": (_i, [_p]),
     "spd_argmax_partial_f32": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p]),

@@ -33,6 +33,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace spd {
 
@@ -243,6 +244,124 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_kernel(ArParams p) {
 #endif
 }
 
+// ------------------------------------------------------------------------------------------------
+// all-reduce FUSED with its consumer: x = sum over ranks of in; residual += x; out = RMSNorm(residual)
+// (tensor_model_parallel_all_reduce after o_proj / down_proj, S/layers/linear.py:1265-1266, followed
+// by fused_add_rmsnorm, S/layers/layernorm.py:46-57) — one kernel instead of two and no round trip
+// of the reduced tensor through memory.  One-shot form: a group of 256 threads owns one token row
+// (two rows per block at a time), reduces it across the W slots, adds the residual and normalises
+// it in registers.  The arithmetic is that of allreduce_kernel followed by rmsnorm_kernel<fused>
+// (elementwise.cu), step by step — fp32 sum in rank order rounded to T, fp32 add of the residual,
+// the same per-thread accumulation order and reduction tree for the sum of squares — so the fused
+// and the unfused path are bit-identical.  Same grid, counters and slots as allreduce_kernel: the
+// calls of one communicator may interleave freely.
+// ------------------------------------------------------------------------------------------------
+struct ArNormParams {
+  void* residual;       // [rows, dim] in / out
+  const void* weight;   // [dim]
+  int64_t rows;
+  int dim;
+  float eps;
+};
+
+constexpr int kArNormMaxVec = 4;  // 16-byte vectors per thread: rows up to 256 * 4 * 8 = 8192 elements
+
+template <typename T>
+__device__ __forceinline__ void ar_unpack8(const int4& v, float (&f)[8]) {
+  const T* h = reinterpret_cast<const T*>(&v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = static_cast<float>(h[i]);
+}
+
+template <typename T, int W>
+__global__ void __launch_bounds__(kArThreads, 1) allreduce_add_rmsnorm_kernel(ArParams p, ArNormParams f) {
+#if __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+  const int world = W > 0 ? W : p.world;
+  uint8_t* self = p.peers.base[p.rank];
+  uint32_t* ctr = counters_of(self);
+  __shared__ uint32_t s_bar, s_call;
+  __shared__ float red[2][33];
+  if (threadIdx.x == 0) {
+    s_bar = ctr[blockIdx.x];
+    s_call = ctr[kArBlocks + blockIdx.x];
+    ctr[blockIdx.x] = s_bar + 1u;
+    ctr[kArBlocks + blockIdx.x] = s_call + 1u;
+  }
+  __syncthreads();
+  const uint32_t bar0 = s_bar;
+  const int parity = s_call & 1u;
+  const int64_t slot_off = kArFlagBytes + kArCounterBytes + parity * p.slot_bytes;
+  const int g = threadIdx.x >> 8;   // row group of the block
+  const int t = threadIdx.x & 255;  // thread within the group == thread of rmsnorm_kernel
+  const int nv = f.dim >> 3;
+  const int4* in = reinterpret_cast<const int4*>(p.in);
+  int4* my_slot = reinterpret_cast<int4*>(self + slot_off);
+  // this block's rows go into its slot region; block b of every peer holds the same rows
+  for (int64_t row = blockIdx.x * 2 + g; row < f.rows; row += 2 * kArBlocks)
+    for (int v = t; v < nv; v += 256) my_slot[row * nv + v] = in[row * nv + v];
+  block_barrier(p, bar0 + 1u);
+
+  int4* out = reinterpret_cast<int4*>(p.out);
+  int4* res = reinterpret_cast<int4*>(f.residual);
+  const int4* wv = reinterpret_cast<const int4*>(f.weight);
+  for (int64_t row = blockIdx.x * 2 + g; row < f.rows; row += 2 * kArBlocks) {
+    float vals[kArNormMaxVec][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kArNormMaxVec; ++i) {
+      const int v = t + i * 256;
+      if (v < nv) {
+        const int64_t idx = row * nv + v;
+        int4 sv[kArMaxRanks];
+#pragma unroll
+        for (int r = 0; r < kArMaxRanks; ++r)
+          if (r < world) sv[r] = __ldcv(reinterpret_cast<const int4*>(p.peers.base[r] + slot_off) + idx);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < kArMaxRanks; ++r)
+          if (r < world) accum8<T>(acc, sv[r]);
+        const int4 x16 = pack8<T>(acc);  // the all-reduce's output, rounded to T as the unfused kernel stores it
+        float rr[8];
+        ar_unpack8<T>(x16, vals[i]);
+        ar_unpack8<T>(res[idx], rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) vals[i][j] += rr[j];
+        res[idx] = pack8<T>(vals[i]);  // residual_out = (x + residual).to(dtype)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += vals[i][j] * vals[i][j];
+      }
+    }
+    // sum of squares over the row: the reduction tree of elementwise.cu's block_sum (8 warps)
+    ss = warp_sum(ss);
+    const int gw = t >> 5;
+    if ((t & 31) == 0) red[g][gw] = ss;
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+    float tt = (t < 8) ? red[g][t] : 0.f;
+    if (gw == 0) {
+      tt = warp_sum(tt);
+      if (t == 0) red[g][32] = tt;
+    }
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+    const float inv = rsqrtf(red[g][32] / static_cast<float>(f.dim) + f.eps);
+#pragma unroll
+    for (int i = 0; i < kArNormMaxVec; ++i) {
+      const int v = t + i * 256;
+      if (v < nv) {
+        float wf[8], o[8];
+        ar_unpack8<T>(wv[v], wf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = vals[i][j] * inv * wf[j];
+        out[row * nv + v] = pack8<T>(o);
+      }
+    }
+  }
+#if __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 // out[r * nvec + i] = rank r's in[i]: the all-gather of equally sized 16-byte-vector payloads
 // (the [bs, 16 B] (max, argmax) rows of the vocab-sharded lm_head; small logits blocks).
 __global__ void __launch_bounds__(kArThreads, 1) allgather_kernel(ArParams p) {
@@ -407,6 +526,50 @@ int spd_allreduce(spd_comm_t* c, void* out, const void* in, int64_t count, int d
     }
   });
 #undef SPD_AR_LAUNCH
+  return 0;
+}
+
+int spd_allreduce_add_rmsnorm(spd_comm_t* c, void* out, const void* in, void* residual, const void* weight,
+                              int64_t rows, int64_t dim, float eps, int dtype, spd_stream_t stream) {
+  SPD_REQUIRE(c && out && in && residual && weight, SPD_E_BADARG, "spd_allreduce_add_rmsnorm: null pointer");
+  SPD_REQUIRE(c->connected, SPD_E_BADARG, "spd_allreduce_add_rmsnorm: communicator is not connected");
+  SPD_REQUIRE(rows >= 0 && dim > 0 && dim % 8 == 0 && dim <= 256 * kArNormMaxVec * 8, SPD_E_SHAPE,
+              "spd_allreduce_add_rmsnorm: dim must be a multiple of 8 up to %d (got %lld)",
+              256 * kArNormMaxVec * 8, (long long)dim);
+  SPD_REQUIRE(aligned16(out) && aligned16(in) && aligned16(residual) && aligned16(weight), SPD_E_ALIGN,
+              "spd_allreduce_add_rmsnorm: pointers must be 16-byte aligned");
+  SPD_REQUIRE(rows * dim * 2 <= c->max_bytes, SPD_E_WORKSPACE,
+              "spd_allreduce_add_rmsnorm: message of %lld bytes exceeds the communicator's %lld",
+              (long long)(rows * dim * 2), (long long)c->max_bytes);
+  if (rows == 0) return 0;
+  ArParams p{};
+  for (int r = 0; r < c->world; ++r) p.peers.base[r] = c->mapped[r];
+  p.rank = c->rank;
+  p.world = c->world;
+  p.slot_bytes = c->max_bytes;
+  p.in = in;
+  p.out = out;
+  p.count = rows * dim;
+  p.timeout_ns = c->timeout_ns;
+  ArNormParams f{};
+  f.residual = residual;
+  f.weight = weight;
+  f.rows = rows;
+  f.dim = static_cast<int>(dim);
+  f.eps = eps;
+  const bool pdl = pdl_enabled();
+  cudaStream_t s = as_stream(stream);
+#define SPD_ARN_LAUNCH(W) \
+  SPD_CUDA(launch(allreduce_add_rmsnorm_kernel<T, W>, dim3(kArBlocks), dim3(kArThreads), 0, s, pdl, p, f))
+  SPD_DISPATCH_DTYPE(dtype, {
+    switch (c->world) {
+      case 2: SPD_ARN_LAUNCH(2); break;
+      case 4: SPD_ARN_LAUNCH(4); break;
+      case 8: SPD_ARN_LAUNCH(8); break;
+      default: SPD_ARN_LAUNCH(0); break;
+    }
+  });
+#undef SPD_ARN_LAUNCH
   return 0;
 }
 

@@ -41,6 +41,14 @@ _DT = {torch.bfloat16: 0, torch.float16: 1}
 # SPD_TP_NCCL=1: messages above SPD_AR_MAX_BYTES and the full-logits all-gather go through
 # torch.distributed's NCCL group instead of slot-sized pieces of the peer-memory kernels (A/B only)
 NCCL_FOR_LARGE = os.environ.get("SPD_TP_NCCL", "0") == "1"
+# the all-reduce after o_proj / down_proj fused with the residual-add RMSNorm that consumes it
+# (decode-sized messages: every rank reads all W slots, so the one-shot form stops paying at ~2 MiB).
+# Bit-identical to the two kernels and tested, but measured NEUTRAL on 2 GPUs (TP = 2 engine, 8B:
+# TPOT p50 at 40 req/s 4.31 ms fused vs 4.22 ms unfused, profiles/r02_bench_n2_fused_ar_norm_ab.txt:
+# the cross-GPU barrier dominates both, and under PDL the separate RMSNorm already starts inside
+# the all-reduce's tail) — so it is opt-in: SPD_FUSE_AR_NORM=1.
+FUSE_AR_NORM = os.environ.get("SPD_FUSE_AR_NORM", "0") == "1"
+FUSE_AR_NORM_MAX_BYTES = int(os.environ.get("SPD_FUSE_AR_NORM_MAX_BYTES", 2 << 20))
 
 
 def init_distributed_environment(tp_size: int, tp_rank: int, backend: str = "nccl",
@@ -128,6 +136,27 @@ class TpComm:
             return x
         dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
         return x
+
+    def all_reduce_add_rmsnorm(self, x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor,
+                               eps: float, force: bool = False) -> bool:
+        """x ← RMSNorm(residual + Σ_ranks x) · weight, residual ← residual + Σ_ranks x, in ONE
+        kernel (`spd_allreduce_add_rmsnorm`); bit-identical to `all_reduce` followed by
+        `ops.fused_add_rmsnorm`.  Returns False — and does nothing — when the fused form does not
+        apply (no peer-memory communicator, a prefill-sized message, an odd layout): the caller
+        then runs the two steps."""
+        if self._h is None or not (FUSE_AR_NORM or force) or x.dtype not in _DT or x.dim() != 2:
+            return False
+        rows, dim = x.shape
+        nbytes = rows * dim * x.element_size()
+        if (nbytes > min(self.max_bytes, FUSE_AR_NORM_MAX_BYTES) or dim % 8 or dim > 8192
+                or not (x.is_contiguous() and residual.is_contiguous() and weight.is_contiguous())
+                or residual.shape != x.shape or residual.dtype != x.dtype or weight.dtype != x.dtype):
+            return False
+        check(lib.spd_allreduce_add_rmsnorm(self._h, x.data_ptr(), x.data_ptr(), residual.data_ptr(),
+                                            weight.data_ptr(), rows, dim, float(eps), _DT[x.dtype],
+                                            torch.cuda.current_stream().cuda_stream),
+              "spd_allreduce_add_rmsnorm")
+        return True
 
     def all_gather(self, x: torch.Tensor) -> torch.Tensor:
         """[rows, n] per rank → [rows, tp * n] (last-dim concat, rank order)."""

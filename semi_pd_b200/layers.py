@@ -27,8 +27,18 @@ class RMSNorm:
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None):
         if residual is not None:
+            if getattr(x, "_spd_pending_all_reduce", False):
+                # x is a RowParallelLinear's partial product whose all-reduce was deferred to here:
+                # one kernel reduces it over the ranks, adds the residual and normalises
+                x._spd_pending_all_reduce = False
+                comm = get_current_comm()
+                if comm is not None and comm.all_reduce_add_rmsnorm(x, residual, self.weight,
+                                                                    self.variance_epsilon):
+                    return x, residual
+                tensor_model_parallel_all_reduce(x)
             ops.fused_add_rmsnorm(x, residual, self.weight, self.variance_epsilon)
             return x, residual
+        assert not getattr(x, "_spd_pending_all_reduce", False)
         return ops.rmsnorm(x, self.weight, self.variance_epsilon)
 
     __call__ = forward
@@ -173,16 +183,22 @@ class MergedColumnParallelLinear(ColumnParallelLinear):
 class RowParallelLinear(LinearBase):
     """input dim sharded; SUM all-reduce of the partial products (layers/linear.py:1250-1272)."""
 
-    def __init__(self, input_size, output_size, reduce_results: bool = True):
+    def __init__(self, input_size, output_size, reduce_results: bool = True, defer_reduce: bool = False):
         tp = get_tensor_model_parallel_world_size()
         super().__init__(input_size // tp, output_size)
         self.reduce_results = reduce_results
+        # defer_reduce: hand the partial product on, marked; the RMSNorm that consumes it (always
+        # a residual-add RMSNorm on the Llama path) runs the all-reduce fused with itself
+        self.defer_reduce = defer_reduce
 
     def forward(self, x: torch.Tensor):
         out = ops.linear(x, self.weight)
         if self.reduce_results and get_tensor_model_parallel_world_size() > 1:
-            # the calling worker's communicator (distributed.set_current_comm): spd_allreduce for
-            # messages up to 8 MiB, ncclAllReduce above
+            if self.defer_reduce:
+                out._spd_pending_all_reduce = True
+                return out, None
+            # the calling worker's communicator (distributed.set_current_comm): the peer-memory
+            # spd_allreduce (in slot-sized pieces for prefill-sized messages)
             out = tensor_model_parallel_all_reduce(out)
         return out, None
 

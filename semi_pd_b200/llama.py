@@ -29,7 +29,7 @@ class LlamaMLP:
         if hidden_act != "silu":
             raise ValueError(f"Unsupported activation: {hidden_act}. Only silu is supported for now.")
         self.gate_up_proj = MergedColumnParallelLinear(hidden_size, [intermediate_size] * 2)
-        self.down_proj = RowParallelLinear(intermediate_size, hidden_size)
+        self.down_proj = RowParallelLinear(intermediate_size, hidden_size, defer_reduce=True)
         self.act_fn = SiluAndMul()
 
     def forward(self, x):
@@ -64,7 +64,7 @@ class LlamaAttention:
         self.scaling = self.head_dim ** -0.5
         self.qkv_proj = QKVParallelLinear(hidden_size, self.head_dim, self.total_num_heads,
                                           self.total_num_kv_heads)
-        self.o_proj = RowParallelLinear(self.total_num_heads * self.head_dim, hidden_size)
+        self.o_proj = RowParallelLinear(self.total_num_heads * self.head_dim, hidden_size, defer_reduce=True)
         self.rotary_emb = get_rope(self.head_dim, rotary_dim=self.head_dim,
                                    max_position=max_position_embeddings, base=rope_theta,
                                    rope_scaling=rope_scaling, is_neox_style=True, dtype=dtype,

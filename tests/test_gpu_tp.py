@@ -85,6 +85,22 @@ def _worker(rank, world, port, use_graph, ret):
         z = y.clone()
         torch.distributed.broadcast(z, src=0)
         assert torch.equal(z, y), (n, algo)
+    # the all-reduce fused with the residual-add RMSNorm that consumes it: bit-identical to the two
+    # separate kernels, eager and replayed from a graph (odd row counts, 70B-wide rows)
+    from semi_pd_b200 import ops
+    for rows, dim in [(1, 512), (3, 4096), (64, 4096), (200, 4096), (37, 8192)]:
+        xp = torch.randn(rows, dim, generator=g, device="cuda", dtype=dtype)
+        res = torch.randn(rows, dim, device="cuda", dtype=dtype)
+        torch.distributed.broadcast(res, src=0)      # the residual stream is replicated
+        wn = (torch.randn(dim, device="cuda") * 0.1 + 1).to(dtype)
+        torch.distributed.broadcast(wn, src=0)
+        xa, ra = comm.all_reduce(xp.clone()), res.clone()
+        ops.fused_add_rmsnorm(xa, ra, wn, 1e-5)
+        xb, rb = xp.clone(), res.clone()
+        assert comm.all_reduce_add_rmsnorm(xb, rb, wn, 1e-5, force=True), (rows, dim)
+        assert torch.equal(xa, xb) and torch.equal(ra, rb), (rows, dim)
+    big = torch.randn(600, 4096, device="cuda", dtype=dtype)
+    assert not comm.all_reduce_add_rmsnorm(big, big.clone(), wn[:4096].contiguous(), 1e-5, force=True)  # prefill-sized
     x = torch.randn(4096 * 8, generator=g, device="cuda", dtype=dtype)
     static_in, ref = x.clone(), x.float().clone()
     torch.distributed.all_reduce(ref)
