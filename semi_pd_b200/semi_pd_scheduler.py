@@ -572,7 +572,7 @@ class SemiPDDecodeScheduler(SemiPDScheduler):
         while self.result_queue and (all_of_them or len(self.result_queue) > keep):
             if service_inbox and self.tp_size == 1:
                 ev = self.result_queue[0][3]
-                while not ev.query():
+                while not ev.query() and not self.stop_flag.is_set():
                     if self.inbox.empty():
                         time.sleep(0.00005)
                     else:
