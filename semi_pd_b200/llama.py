@@ -220,16 +220,13 @@ class LlamaForCausalLM:
         if missing:
             raise KeyError(f"missing parameters: {sorted(missing)[:4]} …")
 
-    def init_dummy_weights(self, seed: int = 1234):
-        """`--load-format dummy`: one generator per parameter as model_loader/weight_utils.py:588-617
-        does, but N(0, 1/fan_in) (norm weights 1 + N(0, 0.1)) instead of U(±1e-3) so logits are
-        O(1) and greedy decoding is well-conditioned.  Generated on the device, full tensor first,
-        then sharded — every TP rank therefore holds slices of the same global weights."""
-        shapes = self.full_shapes()
-        slots = {name: (holder, shard) for name, holder, shard in self.named_slots()}
-        for idx, (name, shape) in enumerate(shapes.items()):
-            if name not in slots:
-                continue
+    def dummy_full_weights(self, seed: int = 1234):
+        """Yields (checkpoint name, FULL tensor) of the `--load-format dummy` model: one generator
+        per parameter as model_loader/weight_utils.py:588-617 does, but N(0, 1/fan_in) (norm
+        weights 1 + N(0, 0.1)) instead of U(±1e-3) so logits are O(1) and greedy decoding is
+        well-conditioned.  Generated on the device; a function of (shapes, seed) only, so every TP
+        rank — and a test's oracle — sees the same global weights."""
+        for idx, (name, shape) in enumerate(self.full_shapes().items()):
             g = torch.Generator(device=self.device)
             g.manual_seed(seed + idx)
             w = torch.randn(shape, generator=g, dtype=torch.float32, device=self.device)
@@ -241,9 +238,17 @@ class LlamaForCausalLM:
                 w = w * (1.5 / math.sqrt(shape[1]))
             else:
                 w = w / math.sqrt(shape[1])
-            holder, shard = slots[name]
-            holder.weight = shard(w.to(self.dtype)).contiguous()
+            yield name, w.to(self.dtype)
             del w
+
+    def init_dummy_weights(self, seed: int = 1234):
+        """Full tensor first, then sharded: every TP rank holds slices of the same global weights."""
+        slots = {name: (holder, shard) for name, holder, shard in self.named_slots()}
+        for name, w in self.dummy_full_weights(seed):
+            if name not in slots:
+                continue
+            holder, shard = slots[name]
+            holder.weight = shard(w).contiguous()
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         """The local (sharded) parameters by checkpoint name."""

@@ -209,3 +209,75 @@ def test_tp2_semi_pd_engine_matches_sequential_oracle():
         mp.spawn(_engine_worker, args=(world, port, ret), nprocs=world, join=True)
         out = dict(ret)
     assert out["bad"] == 0 and out["checked"] > 40, out
+
+
+def _http_tp_main(ret):
+    """TP rank 0 of `python -m sglang.launch_server --enable-semi-pd --tp 2` driven in-process: the
+    FastAPI app (starlette TestClient) on GPU 0, rank 1 spawned by build_app on GPU 1."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from starlette.testclient import TestClient
+
+    from oracle import llama_oracle as O
+    from semi_pd_b200.configs import get_model_config
+    from semi_pd_b200.launch_server import build_app, prepare_server_args
+
+    argv = ["--model-path", "tiny-llama-test", "--enable-semi-pd", "--tp", "2", "--dtype", "float16",
+            "--max-total-tokens", "8192", "--max-running-requests", "16", "--context-length", "512"]
+    sa = prepare_server_args(argv)
+    app, engine = build_app(sa, argv=argv)
+    try:
+        client = TestClient(app)
+        assert client.get("/health").json() == {"status": "ok"}
+        cfg = get_model_config("tiny-llama-test")
+        lens, n_new = [9, 130, 33], 6
+        prompts = [[(5 + 3 * i + 11 * j) % cfg.vocab_size for i in range(n)] for j, n in enumerate(lens)]
+        outs = [client.post("/generate", json={"input_ids": p, "sampling_params": {"max_new_tokens": n_new}}).json()
+                for p in prompts]
+        # the dummy model's GLOBAL weights are a function of (shapes, seed): rebuild them for the oracle
+        model = engine.d_worker.model_runner.model
+        weights = {k: v.cpu() for k, v in model.dummy_full_weights(sa.random_seed)}
+        ocfg = O.OracleLlamaConfig(hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+                                   num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+                                   num_key_value_heads=cfg.num_key_value_heads, head_dim=cfg.head_dim,
+                                   vocab_size=cfg.vocab_size, rms_norm_eps=cfg.rms_norm_eps, rope_theta=cfg.rope_theta,
+                                   max_position_embeddings=cfg.max_position_embeddings)
+        checked = bad = 0
+        for p, body in zip(prompts, outs):
+            assert len(body["output_ids"]) == n_new
+            m = O.LlamaOracle(ocfg, weights, kv_slots=1024, max_reqs=2, max_ctx=520, compute="fp32")
+            s = O.OracleSession(m, 1024, 2)
+            rids, logits, _ = s.extend([p])
+            for k in range(n_new):
+                top2 = logits.topk(2, -1).values[0]
+                if float(top2[0] - top2[1]) <= 2e-2:
+                    break
+                t = int(logits.argmax(-1)[0])
+                bad += int(body["output_ids"][k] != t)
+                checked += 1
+                if k + 1 < n_new:
+                    logits, _ = s.decode(rids, [t])
+        ret["checked"], ret["bad"] = checked, bad
+    finally:
+        engine.shutdown()
+        for pr in engine.tp_followers:
+            pr.join(timeout=60)
+        ret["followers_exited"] = all(not pr.is_alive() for pr in engine.tp_followers)
+
+
+def test_launch_server_tp2_generate_matches_oracle():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    with mp.Manager() as m:
+        ret = m.dict()
+        pr = ctx.Process(target=_http_tp_main, args=(ret,))  # not a daemon: it spawns TP rank 1
+        pr.start()
+        pr.join(timeout=170)
+        alive = pr.is_alive()
+        if alive:
+            pr.kill()
+        out = dict(ret)
+    assert not alive and pr.exitcode == 0, (pr.exitcode, out)
+    assert out["bad"] == 0 and out["checked"] >= 8 and out["followers_exited"], out
