@@ -205,3 +205,70 @@ def test_split_sms_normalises_the_reference_percentages():
     import pytest as _pt
     with _pt.raises(ValueError):
         split_sms(148, 0, 100)
+
+
+def test_decode_scheduler_services_its_inbox_while_a_step_is_running():
+    """`_drain_results(service_inbox=True)`: while the oldest launched step's event has not fired
+    the decode scheduler admits requests / takes prefill reports that arrive, and only then reads
+    the step's ids (TTFT does not pay half a decode step twice).  Driven on CPU with fake events."""
+    import collections
+    import queue
+    import threading
+
+    from semi_pd_b200.semi_pd_scheduler import SemiPDDecodeScheduler
+
+    class FakeEvent:
+        def __init__(self, polls_until_done):
+            self.left = polls_until_done
+
+        def query(self):
+            self.left -= 1
+            return self.left < 0
+
+    s = SemiPDDecodeScheduler.__new__(SemiPDDecodeScheduler)
+    s.tp_size, s.inbox, s.stop_flag = 1, queue.Queue(), threading.Event()
+    s.result_queue = collections.deque()
+    log = []
+    s.recv_requests = lambda: log.append(("recv", s.inbox.get_nowait()))
+    s.maybe_schedule_prefill = lambda: log.append(("schedule",))
+    s.process_batch_result_decode = lambda reqs, pinned, bs, ev: log.append(("result", bs))
+    # two launched steps; keep = 1 -> only the older one is drained
+    s.result_queue.append((["r"], None, 3, FakeEvent(polls_until_done=4)))
+    s.result_queue.append((["r"], None, 5, FakeEvent(polls_until_done=10 ** 9)))
+    s.inbox.put("new request")
+    s._drain_results(keep=1, service_inbox=True)
+    assert log == [("recv", "new request"), ("schedule",), ("result", 3)]
+    assert len(s.result_queue) == 1
+    # without servicing (retraction path / TP lockstep) the inbox is left alone
+    log.clear()
+    s.inbox.put("later")
+    s._drain_results(all_of_them=True)
+    assert log == [("result", 5)] and s.inbox.qsize() == 1
+    # under TP the inbox is only ever processed in lockstep, once per iteration
+    s.tp_size = 2
+    s.result_queue.append((["r"], None, 7, FakeEvent(polls_until_done=3)))
+    log.clear()
+    s._drain_results(all_of_them=True, service_inbox=True)
+    assert log == [("result", 7)] and s.inbox.qsize() == 1
+
+
+def test_http_request_model_parses_token_id_requests():
+    """POST /generate carries token ids (launch_server.GenerateReq, module-level so that FastAPI
+    can resolve it under postponed annotations)."""
+    from fastapi import FastAPI
+    from starlette.testclient import TestClient
+
+    from semi_pd_b200.launch_server import GenerateReq, prepare_server_args
+
+    app = FastAPI()
+
+    @app.post("/generate")
+    def generate(r: GenerateReq):
+        return {"n": len(r.input_ids), "max_new_tokens": (r.sampling_params or {}).get("max_new_tokens")}
+
+    c = TestClient(app)
+    assert c.post("/generate", json={"input_ids": [1, 2, 3], "sampling_params": {"max_new_tokens": 4}}).json() == \
+        {"n": 3, "max_new_tokens": 4}
+    assert c.post("/generate", json={"input_ids": "abc"}).status_code == 422
+    sa = prepare_server_args(["--model-path", "llama-3-8b", "--enable-semi-pd", "--tp", "4"])
+    assert sa.tp_size == 4 and sa.enable_semi_pd and sa.disable_radix_cache and sa.argv[-1] == "4"
